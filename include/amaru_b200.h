@@ -1,0 +1,182 @@
+/*
+ * amaru_b200.h — C ABI of libamaru_b200.so: the B200 (sm_100a) implementation of Amaru.jl's
+ * per-Newton-iteration mechanical hot path (mount_K -> solve_system! -> update_state!).
+ *
+ * The reference is pure Julia and has no FFI for this path today; each entry point below replaces one
+ * Julia call of `mech_stage_solver!` (reference src/mech/mech-solver.jl:186-492) and is what a `ccall`
+ * in the Julia glue binds.  Conventions:
+ *   - every pointer is a HOST pointer, valid only for the duration of the call; the library copies;
+ *   - indices are 0-based at the ABI (the glue subtracts 1 from Julia's eq_id / node ids);
+ *   - every function returns an int status: 0 = ok (ReturnStatus success, src/tools/returnstatus.jl:9),
+ *     >0 = expected failure (ReturnStatus failure; message in `msg`), <0 = usage / CUDA error;
+ *   - `msg`/`msglen`: caller-supplied buffer that receives a NUL-terminated message (may be NULL/0);
+ *   - one opaque handle per analysis stage; a handle is not re-entrant;
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails with
+ *     AMARU_ERR_NO_DEVICE.
+ *
+ * Vector layout at the ABI is the reference's: length ndofs, indexed by eq_id, unknown dofs first
+ * (src/bc.jl:198-233).  IP state layout is element-major (in the order elements are passed, batch after
+ * batch), then integration-point order of the quadrature table (src/mech/mech-solver.jl:245), with
+ * Mandel components (xx, yy, zz, sqrt2*yz, sqrt2*xz, sqrt2*xy) (src/tools/tensors.jl:24-25).
+ */
+#ifndef AMARU_B200_H
+#define AMARU_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* status codes */
+#define AMARU_OK 0
+#define AMARU_FAIL_MATERIAL 1       /* material update failed (von-mises.jl:146)                          */
+#define AMARU_FAIL_NAN 2            /* NaN in internal forces (mech-solver.jl:142)                        */
+#define AMARU_FAIL_SINGULAR 3       /* max|U1| > 1e8, "Possible syngular matrix" (solver.jl:68-71)        */
+#define AMARU_FAIL_NEG_JACOBIAN 4   /* detJ <= 0 (mech-solid.jl:150)                                      */
+#define AMARU_FAIL_CG_NOCONV 5      /* PCG hit maxit before reaching cg_rtol                              */
+#define AMARU_FAIL_TANGENT 6        /* calcD assertion J2 > 0 failed (von-mises.jl:117)                   */
+#define AMARU_ERR_ARG (-1)
+#define AMARU_ERR_CUDA (-2)
+#define AMARU_ERR_NO_DEVICE (-3)
+#define AMARU_ERR_UNSUPPORTED (-4)  /* element / material / stress model outside the hot path             */
+#define AMARU_ERR_COMM (-5)
+
+/* cell shapes (reference src/shape/solids2d.jl, solids3d.jl); default quadrature of each is used */
+#define AMARU_SHAPE_QUAD4 1  /* nn 4,  nd 2, QUAD_IP4 */
+#define AMARU_SHAPE_QUAD8 2  /* nn 8,  nd 2, QUAD_IP4 */
+#define AMARU_SHAPE_HEX8 3   /* nn 8,  nd 3, HEX_IP8  */
+#define AMARU_SHAPE_HEX20 4  /* nn 20, nd 3, HEX_IP8  */
+#define AMARU_SHAPE_TET10 5  /* nn 10, nd 3, TET_IP4  */
+
+/* material kinds; params[8] = {E, nu, p2, p3, p4, rho, 0, 0} */
+#define AMARU_MAT_LINEAR_ELASTIC 1 /* linear-elastic.jl:12-20 : E, nu                                    */
+#define AMARU_MAT_VON_MISES 2      /* von-mises.jl:14-26      : E, nu, fy, H                             */
+#define AMARU_MAT_DRUCKER_PRAGER 3 /* drucker-prager.jl:15-34 : E, nu, alpha, kappa, H                   */
+#define AMARU_MAT_NPARAMS 8
+
+/* stress models accepted (mech-solver.jl:9): everything that uses the 3D constitutive matrix */
+#define AMARU_STRESS_D3 0
+#define AMARU_STRESS_PLANESTRAIN 1
+
+/* preconditioners for the PCG that replaces lu(K11) (solver.jl:42-43) */
+#define AMARU_PRECOND_JACOBI 0
+#define AMARU_PRECOND_BLOCK_JACOBI 1 /* nd x nd node blocks */
+
+typedef struct amaru_model amaru_model; /* opaque */
+
+/* Library / device probe.  Returns the number of visible CUDA devices (0 = none), <0 on error. */
+int amaru_device_count(void);
+const char *amaru_version(void);
+
+/*
+ * Flatten-and-upload: replaces the per-call object walks of the reference — getcoords
+ * (src/element.jl:112-116), the dof-map build (src/mech/elem/mech-solid.jl:160-161), configure_dofs!
+ * (src/bc.jl:198-233) and the `State` vector build (src/mech/mech-solver.jl:245).
+ *
+ *   ndim          2 or 3;  stressmodel AMARU_STRESS_*;  thickness = ctx.thickness (mech-solid.jl:126)
+ *   coords        [nnodes*3] row-major x,y,z
+ *   nbatches      element batches, each of one cell shape (elements sorted by type)
+ *   batch_shape   [nbatches] AMARU_SHAPE_*
+ *   batch_nelem   [nbatches]
+ *   conn          concatenation over batches of [nelem_b * nn_b] node ids, element-major
+ *   elem_mat      [nelem_total] index into the material table
+ *   mat_kind      [nmats] AMARU_MAT_*;  mat_params [nmats*8]
+ *   eqid          [nnodes*ndim] eq_id of (node, ux|uy|uz); unknown dofs are 0..nu-1
+ *   device        CUDA device ordinal
+ * Builds on the device: the element colouring, the symbolic block-CSR pattern, the scatter map.
+ * IP state starts at zero (the IpState constructors, e.g. von-mises.jl:35-42).
+ */
+int amaru_create(int ndim, int stressmodel, double thickness,
+                 int64_t nnodes, const double *coords,
+                 int nbatches, const int32_t *batch_shape, const int64_t *batch_nelem,
+                 const int32_t *conn, const int32_t *elem_mat,
+                 int nmats, const int32_t *mat_kind, const double *mat_params,
+                 const int32_t *eqid, int64_t ndofs, int64_t nu,
+                 int device, amaru_model **out, char *msg, int msglen);
+
+/* Multi-GPU variant: this rank owns `nowned` nodes (local ids 0..nowned-1, the rest are ghosts) and
+ * passes its own + halo elements; `node_gid[nnodes]` are global node ids used to match ghosts with
+ * their owners; `nccl_uid` is the 128-byte ncclUniqueId shared by all ranks.  eqid is global. */
+int amaru_create_partitioned(int ndim, int stressmodel, double thickness,
+                             int64_t nnodes, int64_t nowned, const double *coords, const int64_t *node_gid,
+                             const int32_t *node_owner,
+                             int nbatches, const int32_t *batch_shape, const int64_t *batch_nelem,
+                             const int32_t *conn, const int32_t *elem_mat, const uint8_t *elem_owned,
+                             int nmats, const int32_t *mat_kind, const double *mat_params,
+                             const int32_t *eqid_local, const uint8_t *dof_prescribed,
+                             int64_t ndofs_global, int64_t nu_global,
+                             int rank, int nranks, const void *nccl_uid,
+                             int device, amaru_model **out, char *msg, int msglen);
+int amaru_nccl_unique_id(void *uid128, char *msg, int msglen);
+
+int amaru_destroy(amaru_model *m);
+
+/* sizes */
+int64_t amaru_nip_total(const amaru_model *m);
+int64_t amaru_nnz(const amaru_model *m);       /* scalar non-zeros of the symbolic pattern             */
+int64_t amaru_nblocks(const amaru_model *m);   /* nd x nd blocks stored                                */
+int amaru_ncolors(const amaru_model *m);
+
+/* ip.state in / out (src/mech/mat/linear-elastic.jl:23-34, von-mises.jl:29-43, drucker-prager.jl:46-60).
+ * sigma, eps: [nip_total*6];  epa, dlam: [nip_total] (dlam = Δλ | Δγ; zeros for linear-elastic IPs).
+ * Any pointer may be NULL to skip that field. */
+int amaru_set_state(amaru_model *m, const double *sigma, const double *eps, const double *epa,
+                    const double *dlam, char *msg, int msglen);
+int amaru_get_state(amaru_model *m, double *sigma, double *eps, double *epa, double *dlam, char *msg,
+                    int msglen);
+
+/* copyto!.(StateBk, State) / copyto!.(State, StateBk)  (src/mech/mech-solver.jl:391,333; src/ip.jl:38-52) */
+int amaru_state_backup(amaru_model *m);
+int amaru_state_restore(amaru_model *m);
+
+/* mount_K (src/mech/mech-solver.jl:78-110) with elem_stiffness (src/mech/elem/mech-solid.jl:124-166) and
+ * calcD of the three materials; K stays on the device. */
+int amaru_assemble_K(amaru_model *m, char *msg, int msglen);
+
+/* Symbolic CSR pattern in eq_id numbering (== the CSC of the reference's symbolic K, which is structurally
+ * symmetric) and the assembled values.  rowptr [ndofs+1], colind/val [nnz], columns ascending per row.
+ * val may be NULL (pattern only).  For parity tests and for callers that want K back. */
+int amaru_get_csr(amaru_model *m, int64_t *rowptr, int32_t *colind, double *val, char *msg, int msglen);
+
+/* solve_system!(K, U, F, nu) (src/solver.jl:5-79): on entry U[nu:] holds prescribed values and F[:nu] the
+ * known forces; on return U[:nu] is the solution and F[nu:] the reactions (solver.jl:74-75).  lu(K11) is
+ * replaced by a preconditioned CG on the device, stopped at ||r|| <= cg_rtol*||b||.
+ * iters / relres (may be NULL) receive the CG iteration count and final relative residual. */
+int amaru_solve(amaru_model *m, double *U, double *F, double cg_rtol, int cg_maxit, int precond,
+                int *iters, double *relres, char *msg, int msglen);
+
+/* update_state!(active_elems, ΔUt, t) (src/mech/mech-solver.jl:124-144) with update_elem!
+ * (src/mech/elem/mech-solid.jl:243-279) and the material update_state! functions; mutates the device IP
+ * state and returns ΔFin[ndofs]. */
+int amaru_update_state(amaru_model *m, const double *dU, double *dFin, char *msg, int msglen);
+
+/* elem_internal_forces (src/mech/elem/mech-solid.jl:208-240) summed over all elements: Fin[ndofs]. */
+int amaru_internal_forces(amaru_model *m, double *Fin, char *msg, int msglen);
+
+/* ---- next tier: Newmark dynamics (src/mech/dyn-solver.jl:72-103,373-399) -------------------- */
+/* mount_M with elem_mass (mech-solid.jl:169-205); rho[nelem_total]. M uses K's pattern. */
+int amaru_assemble_M(amaru_model *m, const double *rho, char *msg, int msglen);
+/* The matrix used by amaru_solve / amaru_matvec becomes  a*K + b*M  (Kp = K + 4/Δt² M + 2/Δt C with
+ * C = αM + βK folds into two scalars, dyn-solver.jl:376-377). a=1,b=0 restores plain K. */
+int amaru_set_system_matrix(amaru_model *m, double a, double b, char *msg, int msglen);
+/* y = (a*K + b*M) x over all ndofs (eq_id ordering), e.g. M*A, C*V products of dyn-solver.jl:378,399 */
+int amaru_matvec(amaru_model *m, double a, double b, const double *x, double *y, char *msg, int msglen);
+
+/* ---- measurement hooks (bench.py): device-resident Newton iteration, no host copies ----------- */
+/* One assemble_K + solve + state_restore + update_state with U/F/dFin kept on the device; returns the
+ * CUDA-event time of each phase in ms (4 doubles: assemble, solve, update, total) and CG iterations. */
+int amaru_newton_iteration_device(amaru_model *m, double cg_rtol, int cg_maxit, int precond,
+                                  double *phase_ms, int *iters, double *relres, char *msg, int msglen);
+/* Upload the vectors used by amaru_newton_iteration_device (U: prescribed values, F: known forces). */
+int amaru_set_device_vectors(amaru_model *m, const double *U, const double *F, char *msg, int msglen);
+/* time `reps` launches of one kernel class on the model's stream (CUDA events); kind: 0 SpMV, 1 assemble,
+ * 2 update_state, 3 fused CG vector update, 4 p-update. Returns average ms per launch. */
+int amaru_time_kernel(amaru_model *m, int kind, int precond, int reps, double *avg_ms, char *msg, int msglen);
+/* number of kernels launched by this handle since creation (the bench's gpu_launches claim) */
+int64_t amaru_launch_count(const amaru_model *m);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AMARU_B200_H */
