@@ -1,0 +1,628 @@
+// extern "C" surface of libamaru_b200.so (include/amaru_b200.h).  Each entry point replaces one Julia call of the
+// reference's mech_stage_solver! (src/mech/mech-solver.jl:186-492); see the header for the mapping.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <numeric>
+
+#include "amaru_internal.h"
+
+namespace {
+
+void set_msg(char *msg, int msglen, const std::string &s) {
+    if (msg && msglen > 0) {
+        std::snprintf(msg, (size_t)msglen, "%s", s.c_str());
+    }
+}
+
+template <class F>
+int guarded(char *msg, int msglen, F f) {
+    try {
+        set_msg(msg, msglen, "");
+        return f();
+    } catch (const AmaruError &e) {
+        set_msg(msg, msglen, e.msg);
+        return e.code;
+    } catch (const std::exception &e) {
+        set_msg(msg, msglen, e.what());
+        return AMARU_ERR_ARG;
+    }
+}
+
+template <class T>
+T *upload(const T *h, size_t n) {
+    T *d = nullptr;
+    CUDA_CHECK(cudaMalloc(&d, std::max<size_t>(n, 1) * sizeof(T)));
+    if (n) CUDA_CHECK(cudaMemcpy(d, h, n * sizeof(T), cudaMemcpyHostToDevice));
+    return d;
+}
+
+void use_device(const amaru_model *m) { CUDA_CHECK(cudaSetDevice(m->device)); }
+
+const char *status_text(int st) {
+    switch (st) {
+    case AMARU_FAIL_MATERIAL: return "VonMisses: Negative value for √J2D";   // von-mises.jl:146
+    case AMARU_FAIL_NAN: return "solve_system!: NaN values in internal forces vector";  // mech-solver.jl:142
+    case AMARU_FAIL_SINGULAR: return "solve_system!: Possible syngular matrix";          // solver.jl:70
+    case AMARU_FAIL_NEG_JACOBIAN: return "Negative Jacobian determinant in cell";        // mech-solid.jl:150
+    case AMARU_FAIL_CG_NOCONV: return "solve_system!: PCG did not reach cg_rtol within cg_maxit iterations";
+    case AMARU_FAIL_TANGENT: return "AssertionError: j2d > 0";                           // von-mises.jl:117
+    }
+    return "";
+}
+
+int read_status(amaru_model *m) {
+    int st = 0;
+    CUDA_CHECK(cudaMemcpyAsync(&st, m->d_status, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+    CUDA_CHECK(cudaStreamSynchronize(m->stream));
+    return st;
+}
+void reset_status(amaru_model *m) { CUDA_CHECK(cudaMemsetAsync(m->d_status, 0, sizeof(int), m->stream)); }
+
+struct CreateArgs {
+    int ndim, stressmodel;
+    double thickness;
+    int64_t nnodes, nowned;
+    const double *coords;
+    int nbatches;
+    const int32_t *batch_shape;
+    const int64_t *batch_nelem;
+    const int32_t *conn;
+    const int32_t *elem_mat;
+    int nmats;
+    const int32_t *mat_kind;
+    const double *mat_params;
+    const int32_t *eqid;
+    const uint8_t *prescribed;   // optional (partitioned); else eqid >= nu
+    int64_t ndofs, nu;
+    int device;
+    int rank, nranks;
+};
+
+amaru_model *create_impl(const CreateArgs &a) {
+    AMARU_REQUIRE(a.ndim == 2 || a.ndim == 3, AMARU_ERR_ARG, "amaru_create: ndim must be 2 or 3");
+    AMARU_REQUIRE(a.stressmodel == AMARU_STRESS_D3 || a.stressmodel == AMARU_STRESS_PLANESTRAIN, AMARU_ERR_UNSUPPORTED,
+                  "amaru_create: only the d3 / planestrain stress models are on the B200 hot path (no CPU fallback)");
+    AMARU_REQUIRE(a.nnodes > 0 && a.nbatches > 0 && a.nmats > 0, AMARU_ERR_ARG, "amaru_create: empty model");
+    AMARU_REQUIRE(a.coords && a.conn && a.elem_mat && a.mat_kind && a.mat_params && a.eqid && a.batch_shape &&
+                      a.batch_nelem, AMARU_ERR_ARG, "amaru_create: null pointer");
+    AMARU_REQUIRE(a.thickness > 0, AMARU_ERR_ARG, "amaru_create: thickness must be > 0");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        throw AmaruError{AMARU_ERR_NO_DEVICE, "amaru_create: no CUDA device visible; this library has no CPU fallback"};
+    AMARU_REQUIRE(a.device >= 0 && a.device < ndev, AMARU_ERR_ARG, "amaru_create: bad device ordinal");
+    for (int i = 0; i < a.nmats; i++) {
+        const int k = a.mat_kind[i];
+        AMARU_REQUIRE(k == AMARU_MAT_LINEAR_ELASTIC || k == AMARU_MAT_VON_MISES || k == AMARU_MAT_DRUCKER_PRAGER,
+                      AMARU_ERR_UNSUPPORTED, "amaru_create: material outside the hot path (LinearElastic, VonMises, DruckerPrager)");
+    }
+
+    std::unique_ptr<amaru_model> mp(new amaru_model());
+    amaru_model *m = mp.get();
+    m->device = a.device;
+    CUDA_CHECK(cudaSetDevice(a.device));
+    cudaDeviceProp prop;
+    CUDA_CHECK(cudaGetDeviceProperties(&prop, a.device));
+    m->nsm = prop.multiProcessorCount;
+    CUDA_CHECK(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
+    m->ndim = m->nd = a.ndim;
+    m->stressmodel = a.stressmodel;
+    m->th = a.thickness;
+    m->nnodes = a.nnodes;
+    m->nowned = a.nowned;
+    m->ndofs = a.ndofs;
+    m->nu = a.nu;
+    m->nmats = a.nmats;
+    m->rank = a.rank;
+    m->nranks = a.nranks;
+
+    // batches
+    std::vector<ShapeInfo> info(a.nbatches);
+    std::vector<int> nn(a.nbatches);
+    std::vector<const int32_t *> connp(a.nbatches);
+    int64_t eoff = 0, coff = 0, ipoff = 0;
+    m->batches.resize(a.nbatches);
+    for (int b = 0; b < a.nbatches; b++) {
+        AMARU_REQUIRE(amaru_shape_info(a.batch_shape[b], info[b]), AMARU_ERR_UNSUPPORTED,
+                      "amaru_create: cell shape outside the hot path (QUAD4, QUAD8, HEX8, HEX20, TET10)");
+        AMARU_REQUIRE(info[b].nd == a.ndim, AMARU_ERR_ARG, "amaru_create: cell shape dimension differs from ndim");
+        Batch &B = m->batches[b];
+        B.shape = info[b].id; B.nn = info[b].nn; B.nd = info[b].nd; B.nip = info[b].nip;
+        B.nelem = a.batch_nelem[b];
+        B.elem_off = eoff;
+        B.ip_off = ipoff;
+        nn[b] = B.nn;
+        connp[b] = a.conn + coff;
+        for (int64_t i = 0; i < B.nelem * B.nn; i++)
+            AMARU_REQUIRE(connp[b][i] >= 0 && connp[b][i] < a.nnodes, AMARU_ERR_ARG, "amaru_create: node id out of range");
+        eoff += B.nelem;
+        coff += B.nelem * B.nn;
+        ipoff += B.nelem * B.nip;
+    }
+    m->nelem_total = eoff;
+    m->nip_total = ipoff;
+    for (int64_t e = 0; e < eoff; e++)
+        AMARU_REQUIRE(a.elem_mat[e] >= 0 && a.elem_mat[e] < a.nmats, AMARU_ERR_ARG, "amaru_create: material index out of range");
+
+    // host preprocessing: adjacency, colouring, symbolic pattern
+    std::vector<int64_t> adj_ptr, adj;
+    amaru_build_adjacency(a.nnodes, a.nbatches, nn.data(), a.batch_nelem, connp.data(), adj_ptr, adj);
+    std::vector<int32_t> color;
+    m->ncolors = amaru_color_elements(a.nnodes, a.nbatches, nn.data(), a.batch_nelem, connp.data(), adj_ptr, adj, color);
+    AMARU_REQUIRE(m->ncolors > 0, AMARU_ERR_ARG, "amaru_create: element colouring needs more than 512 colours");
+    HostPattern pat;
+    amaru_build_pattern(a.nowned, a.nbatches, nn.data(), a.batch_nelem, connp.data(), adj_ptr, adj, pat);
+    m->nblk = (int64_t)pat.col.size();
+
+    // colour-sort each batch (stable: ascending element id inside a colour)
+    for (int b = 0; b < a.nbatches; b++) {
+        Batch &B = m->batches[b];
+        const int32_t *col_b = color.data() + B.elem_off;
+        std::vector<int64_t> cnt((size_t)m->ncolors + 1, 0);
+        for (int64_t e = 0; e < B.nelem; e++) cnt[(size_t)col_b[e] + 1]++;
+        for (int c = 0; c < m->ncolors; c++) cnt[c + 1] += cnt[c];
+        B.color_off.assign(cnt.begin(), cnt.end());
+        std::vector<int64_t> perm((size_t)B.nelem);
+        {
+            std::vector<int64_t> fill(cnt.begin(), cnt.end() - 1);
+            for (int64_t e = 0; e < B.nelem; e++) perm[(size_t)fill[col_b[e]]++] = e;
+        }
+        std::vector<int32_t> sconn((size_t)B.nelem * B.nn), smat((size_t)B.nelem);
+        for (int64_t s = 0; s < B.nelem; s++) {
+            const int64_t e = perm[(size_t)s];
+            std::memcpy(&sconn[(size_t)s * B.nn], connp[b] + e * B.nn, sizeof(int32_t) * B.nn);
+            smat[(size_t)s] = a.elem_mat[B.elem_off + e];
+        }
+        B.d_conn = upload(sconn.data(), sconn.size());
+        B.d_emat = upload(smat.data(), smat.size());
+        B.d_perm = upload(perm.data(), perm.size());
+        B.d_dNdR = upload(info[b].dNdR.data(), info[b].dNdR.size());
+        B.d_N = upload(info[b].N.data(), info[b].N.size());
+        std::vector<double> w((size_t)B.nip);
+        for (int q = 0; q < B.nip; q++) w[q] = info[b].ips[4 * q + 3];
+        B.d_w = upload(w.data(), w.size());
+        CUDA_CHECK(cudaMalloc(&B.d_map, std::max<size_t>((size_t)B.nelem * B.nn * B.nn, 1) * sizeof(int32_t)));
+    }
+
+    // model arrays
+    m->d_coords = upload(a.coords, (size_t)a.nnodes * 3);
+    m->d_eqid = upload(a.eqid, (size_t)a.nnodes * m->nd);
+    {
+        std::vector<uint8_t> fx((size_t)a.nnodes * m->nd);
+        for (size_t i = 0; i < fx.size(); i++) {
+            AMARU_REQUIRE(a.eqid[i] >= 0 && a.eqid[i] < a.ndofs, AMARU_ERR_ARG, "amaru_create: eq_id out of range");
+            fx[i] = a.prescribed ? a.prescribed[i] : (uint8_t)(a.eqid[i] >= a.nu);
+        }
+        m->d_fixed = upload(fx.data(), fx.size());
+    }
+    m->d_mat_kind = upload(a.mat_kind, (size_t)a.nmats);
+    m->d_mat_par = upload(a.mat_params, (size_t)a.nmats * AMARU_MAT_NPARAMS);
+    m->h_eqid.assign(a.eqid, a.eqid + (size_t)a.nnodes * m->nd);
+
+    // pattern + matrix
+    m->d_rowptr = upload(pat.rowptr.data(), pat.rowptr.size());
+    m->d_col = upload(pat.col.data(), pat.col.size());
+    m->d_diag = upload(pat.diag.data(), pat.diag.size());
+    m->h_rowptr.swap(pat.rowptr);
+    m->h_col.swap(pat.col);
+    const size_t kbytes = std::max<size_t>((size_t)m->nblk * m->nd * m->nd, 1) * sizeof(double);
+    CUDA_CHECK(cudaMalloc(&m->d_K, kbytes));
+    CUDA_CHECK(cudaMemset(m->d_K, 0, kbytes));
+    m->d_A = m->d_K;
+    for (Batch &B : m->batches) amaru_build_map(m, B);
+
+    // IP state
+    const size_t sbytes = std::max<size_t>((size_t)AMARU_NSTATE * m->nip_total, 1) * sizeof(double);
+    CUDA_CHECK(cudaMalloc(&m->d_state, sbytes));
+    CUDA_CHECK(cudaMalloc(&m->d_statebk, sbytes));
+    CUDA_CHECK(cudaMemset(m->d_state, 0, sbytes));
+    CUDA_CHECK(cudaMemset(m->d_statebk, 0, sbytes));
+
+    // staging
+    m->io_len = std::max<int64_t>(m->ndofs, 6 * m->nip_total);
+    CUDA_CHECK(cudaMalloc(&m->d_io, (size_t)m->io_len * sizeof(double)));
+    CUDA_CHECK(cudaMalloc(&m->d_U, (size_t)m->ndofs * sizeof(double)));
+    CUDA_CHECK(cudaMalloc(&m->d_F, (size_t)m->ndofs * sizeof(double)));
+    CUDA_CHECK(cudaMemset(m->d_U, 0, (size_t)m->ndofs * sizeof(double)));
+    CUDA_CHECK(cudaMemset(m->d_F, 0, (size_t)m->ndofs * sizeof(double)));
+    CUDA_CHECK(cudaMalloc(&m->d_status, sizeof(int)));
+    CUDA_CHECK(cudaMemset(m->d_status, 0, sizeof(int)));
+    amaru_pcg_setup(m);
+    CUDA_CHECK(cudaStreamSynchronize(m->stream));
+    return mp.release();
+}
+
+void free_model(amaru_model *m) {
+    cudaSetDevice(m->device);
+    if (m->stream) cudaStreamSynchronize(m->stream);
+    for (Batch &B : m->batches) {
+        cudaFree(B.d_conn); cudaFree(B.d_emat); cudaFree(B.d_map); cudaFree(B.d_perm); cudaFree(B.d_owned);
+        cudaFree(B.d_rho); cudaFree(B.d_dNdR); cudaFree(B.d_N); cudaFree(B.d_w);
+    }
+    if (m->d_A && m->d_A != m->d_K) cudaFree(m->d_A);
+    for (void *p : {(void *)m->d_coords, (void *)m->d_eqid, (void *)m->d_fixed, (void *)m->d_mat_kind, (void *)m->d_mat_par,
+                    (void *)m->d_rowptr, (void *)m->d_col, (void *)m->d_diag, (void *)m->d_K, (void *)m->d_M,
+                    (void *)m->d_Minv, (void *)m->d_state, (void *)m->d_statebk, (void *)m->d_x, (void *)m->d_r,
+                    (void *)m->d_z, (void *)m->d_p, (void *)m->d_q, (void *)m->d_b, (void *)m->d_f, (void *)m->d_io,
+                    (void *)m->d_U, (void *)m->d_F, (void *)m->d_partial, (void *)m->d_scal, (void *)m->d_status})
+        cudaFree(p);
+    if (m->h_pinned) cudaFreeHost(m->h_pinned);
+    if (m->stream) cudaStreamDestroy(m->stream);
+    delete m;
+}
+
+// core of amaru_solve on device-resident ABI-order vectors d_U / d_F
+int solve_device(amaru_model *m, double cg_rtol, int cg_maxit, int precond, SolveInfo &info) {
+    amaru_eq_to_nodes(m, m->d_U, m->d_x);
+    amaru_eq_to_nodes(m, m->d_F, m->d_b);
+    amaru_pcg_solve(m, cg_rtol, cg_maxit, precond, info);
+    amaru_nodes_to_eq(m, m->d_x, m->d_U, 1);   // U[1:nu]     .= U1   (solver.jl:74)
+    amaru_nodes_to_eq(m, m->d_q, m->d_F, 2);   // F[nu+1:end] .= F2   (solver.jl:75)
+    if (!info.converged) return AMARU_FAIL_CG_NOCONV;
+    if (!(info.maxabs <= 1e8)) return AMARU_FAIL_SINGULAR;   // solver.jl:68-71 (NaN also lands here)
+    return AMARU_OK;
+}
+
+int update_device(amaru_model *m) {
+    reset_status(m);
+    amaru_eq_to_nodes(m, m->d_U, m->d_x);
+    amaru_launch_update(m, m->d_x, m->d_f, 0);
+    CUDA_CHECK(cudaMemsetAsync(m->d_F, 0, (size_t)m->ndofs * sizeof(double), m->stream));
+    amaru_nodes_to_eq(m, m->d_f, m->d_F, 0);
+    const int st = read_status(m);
+    if (st) return st;
+    if (amaru_check_nan(m, m->d_f, m->nowned * m->nd)) return AMARU_FAIL_NAN;
+    return AMARU_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int amaru_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+const char *amaru_version(void) { return "amaru_b200 0.1 (sm_100a)"; }
+
+int amaru_create(int ndim, int stressmodel, double thickness, int64_t nnodes, const double *coords, int nbatches,
+                 const int32_t *batch_shape, const int64_t *batch_nelem, const int32_t *conn, const int32_t *elem_mat,
+                 int nmats, const int32_t *mat_kind, const double *mat_params, const int32_t *eqid, int64_t ndofs,
+                 int64_t nu, int device, amaru_model **out, char *msg, int msglen) {
+    return guarded(msg, msglen, [&]() {
+        AMARU_REQUIRE(out != nullptr, AMARU_ERR_ARG, "amaru_create: out is NULL");
+        *out = nullptr;
+        AMARU_REQUIRE(ndofs == nnodes * ndim, AMARU_ERR_ARG, "amaru_create: ndofs must equal nnodes*ndim");
+        AMARU_REQUIRE(nu >= 0 && nu <= ndofs, AMARU_ERR_ARG, "amaru_create: nu out of range");
+        CreateArgs a{ndim, stressmodel, thickness, nnodes, nnodes, coords, nbatches, batch_shape, batch_nelem, conn,
+                     elem_mat, nmats, mat_kind, mat_params, eqid, nullptr, ndofs, nu, device, 0, 1};
+        *out = create_impl(a);
+        return AMARU_OK;
+    });
+}
+
+int amaru_destroy(amaru_model *m) {
+    if (!m) return AMARU_ERR_ARG;
+    free_model(m);
+    return AMARU_OK;
+}
+
+int64_t amaru_nip_total(const amaru_model *m) { return m ? m->nip_total : -1; }
+int64_t amaru_nnz(const amaru_model *m) { return m ? m->nblk * m->nd * m->nd : -1; }
+int64_t amaru_nblocks(const amaru_model *m) { return m ? m->nblk : -1; }
+int amaru_ncolors(const amaru_model *m) { return m ? m->ncolors : -1; }
+int64_t amaru_launch_count(const amaru_model *m) { return m ? m->launches : -1; }
+
+int amaru_set_state(amaru_model *m, const double *sigma, const double *eps, const double *epa, const double *dlam,
+                    char *msg, int msglen) {
+    return guarded(msg, msglen, [&]() {
+        AMARU_REQUIRE(m, AMARU_ERR_ARG, "null handle");
+        use_device(m);
+        const int64_t n = m->nip_total;
+        struct F { const double *h; int plane0, ncomp; } fields[4] = {{sigma, 0, 6}, {eps, 6, 6}, {epa, 12, 1}, {dlam, 13, 1}};
+        for (auto &f : fields) {
+            if (!f.h) continue;
+            CUDA_CHECK(cudaMemcpyAsync(m->d_io, f.h, (size_t)n * f.ncomp * sizeof(double), cudaMemcpyHostToDevice, m->stream));
+            amaru_state_permute(m, m->d_io, f.plane0, f.ncomp, true);
+            CUDA_CHECK(cudaStreamSynchronize(m->stream));
+        }
+        return AMARU_OK;
+    });
+}
+
+int amaru_get_state(amaru_model *m, double *sigma, double *eps, double *epa, double *dlam, char *msg, int msglen) {
+    return guarded(msg, msglen, [&]() {
+        AMARU_REQUIRE(m, AMARU_ERR_ARG, "null handle");
+        use_device(m);
+        const int64_t n = m->nip_total;
+        struct F { double *h; int plane0, ncomp; } fields[4] = {{sigma, 0, 6}, {eps, 6, 6}, {epa, 12, 1}, {dlam, 13, 1}};
+        for (auto &f : fields) {
+            if (!f.h) continue;
+            amaru_state_permute(m, m->d_io, f.plane0, f.ncomp, false);
+            CUDA_CHECK(cudaMemcpyAsync(f.h, m->d_io, (size_t)n * f.ncomp * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
+            CUDA_CHECK(cudaStreamSynchronize(m->stream));
+        }
+        return AMARU_OK;
+    });
+}
+
+int amaru_state_backup(amaru_model *m) {
+    if (!m) return AMARU_ERR_ARG;
+    cudaSetDevice(m->device);
+    const size_t bytes = (size_t)AMARU_NSTATE * m->nip_total * sizeof(double);
+    if (cudaMemcpyAsync(m->d_statebk, m->d_state, bytes, cudaMemcpyDeviceToDevice, m->stream) != cudaSuccess) return AMARU_ERR_CUDA;
+    return AMARU_OK;
+}
+
+int amaru_state_restore(amaru_model *m) {
+    if (!m) return AMARU_ERR_ARG;
+    cudaSetDevice(m->device);
+    const size_t bytes = (size_t)AMARU_NSTATE * m->nip_total * sizeof(double);
+    if (cudaMemcpyAsync(m->d_state, m->d_statebk, bytes, cudaMemcpyDeviceToDevice, m->stream) != cudaSuccess) return AMARU_ERR_CUDA;
+    return AMARU_OK;
+}
+
+int amaru_assemble_K(amaru_model *m, char *msg, int msglen) {
+    return guarded(msg, msglen, [&]() {
+        AMARU_REQUIRE(m, AMARU_ERR_ARG, "null handle");
+        use_device(m);
+        reset_status(m);
+        amaru_launch_assemble(m, 0);
+        amaru_combine_matrix(m);
+        const int st = read_status(m);
+        if (st) throw AmaruError{st, status_text(st)};
+        return AMARU_OK;
+    });
+}
+
+int amaru_assemble_M(amaru_model *m, const double *rho, char *msg, int msglen) {
+    return guarded(msg, msglen, [&]() {
+        AMARU_REQUIRE(m && rho, AMARU_ERR_ARG, "null argument");
+        use_device(m);
+        reset_status(m);
+        if (!m->d_M) CUDA_CHECK(cudaMalloc(&m->d_M, (size_t)m->nblk * m->nd * m->nd * sizeof(double)));
+        for (Batch &B : m->batches) {
+            std::vector<int64_t> perm((size_t)B.nelem);
+            CUDA_CHECK(cudaMemcpy(perm.data(), B.d_perm, perm.size() * sizeof(int64_t), cudaMemcpyDeviceToHost));
+            std::vector<double> r((size_t)B.nelem);
+            for (int64_t s = 0; s < B.nelem; s++) r[(size_t)s] = rho[B.elem_off + perm[(size_t)s]];
+            if (B.d_rho) cudaFree(B.d_rho);
+            B.d_rho = upload(r.data(), r.size());
+        }
+        amaru_launch_assemble(m, 1);
+        const int st = read_status(m);
+        if (st) throw AmaruError{st, status_text(st)};
+        return AMARU_OK;
+    });
+}
+
+int amaru_set_system_matrix(amaru_model *m, double a, double b, char *msg, int msglen) {
+    return guarded(msg, msglen, [&]() {
+        AMARU_REQUIRE(m, AMARU_ERR_ARG, "null handle");
+        use_device(m);
+        m->sysA = a;
+        m->sysB = b;
+        amaru_combine_matrix(m);
+        CUDA_CHECK(cudaStreamSynchronize(m->stream));
+        return AMARU_OK;
+    });
+}
+
+int amaru_get_csr(amaru_model *m, int64_t *rowptr, int32_t *colind, double *val, char *msg, int msglen) {
+    return guarded(msg, msglen, [&]() {
+        AMARU_REQUIRE(m && rowptr && colind, AMARU_ERR_ARG, "null argument");
+        AMARU_REQUIRE(m->nranks == 1, AMARU_ERR_UNSUPPORTED, "amaru_get_csr: single-GPU handles only");
+        use_device(m);
+        const int bs = m->nd, b2 = bs * bs;
+        std::vector<double> K;
+        if (val) {
+            K.resize((size_t)m->nblk * b2);
+            CUDA_CHECK(cudaStreamSynchronize(m->stream));
+            CUDA_CHECK(cudaMemcpy(K.data(), m->d_A, K.size() * sizeof(double), cudaMemcpyDeviceToHost));
+        }
+        const int64_t n = m->ndofs;
+        std::vector<int64_t> cnt((size_t)n + 1, 0);
+        for (int64_t A = 0; A < m->nowned; A++) {
+            const int64_t nb = m->h_rowptr[A + 1] - m->h_rowptr[A];
+            for (int r = 0; r < bs; r++) cnt[(size_t)m->h_eqid[A * bs + r] + 1] = nb * bs;
+        }
+        for (int64_t i = 0; i < n; i++) cnt[i + 1] += cnt[i];
+        std::memcpy(rowptr, cnt.data(), (size_t)(n + 1) * sizeof(int64_t));
+        std::vector<std::pair<int32_t, double>> row;
+        for (int64_t A = 0; A < m->nowned; A++) {
+            for (int r = 0; r < bs; r++) {
+                row.clear();
+                for (int32_t k = m->h_rowptr[A]; k < m->h_rowptr[A + 1]; k++) {
+                    const int64_t B = m->h_col[k];
+                    for (int c = 0; c < bs; c++)
+                        row.emplace_back(m->h_eqid[B * bs + c], val ? K[(size_t)k * b2 + r * bs + c] : 0.0);
+                }
+                std::sort(row.begin(), row.end(), [](const auto &x, const auto &y) { return x.first < y.first; });
+                int64_t o = cnt[(size_t)m->h_eqid[A * bs + r]];
+                for (auto &e : row) {
+                    colind[o] = e.first;
+                    if (val) val[o] = e.second;
+                    o++;
+                }
+            }
+        }
+        return AMARU_OK;
+    });
+}
+
+int amaru_solve(amaru_model *m, double *U, double *F, double cg_rtol, int cg_maxit, int precond, int *iters,
+                double *relres, char *msg, int msglen) {
+    return guarded(msg, msglen, [&]() {
+        AMARU_REQUIRE(m && U && F, AMARU_ERR_ARG, "null argument");
+        AMARU_REQUIRE(cg_rtol > 0 && cg_maxit > 0, AMARU_ERR_ARG, "amaru_solve: cg_rtol and cg_maxit must be > 0");
+        AMARU_REQUIRE(precond == AMARU_PRECOND_JACOBI || precond == AMARU_PRECOND_BLOCK_JACOBI, AMARU_ERR_ARG, "bad preconditioner");
+        use_device(m);
+        const size_t bytes = (size_t)m->ndofs * sizeof(double);
+        CUDA_CHECK(cudaMemcpyAsync(m->d_U, U, bytes, cudaMemcpyHostToDevice, m->stream));
+        CUDA_CHECK(cudaMemcpyAsync(m->d_F, F, bytes, cudaMemcpyHostToDevice, m->stream));
+        SolveInfo info;
+        const int st = solve_device(m, cg_rtol, cg_maxit, precond, info);
+        if (iters) *iters = info.iters;
+        if (relres) *relres = info.relres;
+        if (st == AMARU_FAIL_CG_NOCONV || st == AMARU_FAIL_SINGULAR) throw AmaruError{st, status_text(st)};
+        if (m->nu > 0) CUDA_CHECK(cudaMemcpyAsync(U, m->d_U, (size_t)m->nu * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
+        if (m->ndofs > m->nu)
+            CUDA_CHECK(cudaMemcpyAsync(F + m->nu, m->d_F + m->nu, (size_t)(m->ndofs - m->nu) * sizeof(double),
+                                       cudaMemcpyDeviceToHost, m->stream));
+        CUDA_CHECK(cudaStreamSynchronize(m->stream));
+        return st;
+    });
+}
+
+int amaru_update_state(amaru_model *m, const double *dU, double *dFin, char *msg, int msglen) {
+    return guarded(msg, msglen, [&]() {
+        AMARU_REQUIRE(m && dU && dFin, AMARU_ERR_ARG, "null argument");
+        use_device(m);
+        const size_t bytes = (size_t)m->ndofs * sizeof(double);
+        CUDA_CHECK(cudaMemcpyAsync(m->d_U, dU, bytes, cudaMemcpyHostToDevice, m->stream));
+        const int st = update_device(m);
+        CUDA_CHECK(cudaMemcpyAsync(dFin, m->d_F, bytes, cudaMemcpyDeviceToHost, m->stream));
+        CUDA_CHECK(cudaStreamSynchronize(m->stream));
+        if (st) throw AmaruError{st, status_text(st)};
+        return AMARU_OK;
+    });
+}
+
+int amaru_internal_forces(amaru_model *m, double *Fin, char *msg, int msglen) {
+    return guarded(msg, msglen, [&]() {
+        AMARU_REQUIRE(m && Fin, AMARU_ERR_ARG, "null argument");
+        use_device(m);
+        amaru_launch_update(m, m->d_x, m->d_f, 1);
+        CUDA_CHECK(cudaMemsetAsync(m->d_F, 0, (size_t)m->ndofs * sizeof(double), m->stream));
+        amaru_nodes_to_eq(m, m->d_f, m->d_F, 0);
+        CUDA_CHECK(cudaMemcpyAsync(Fin, m->d_F, (size_t)m->ndofs * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
+        CUDA_CHECK(cudaStreamSynchronize(m->stream));
+        return AMARU_OK;
+    });
+}
+
+int amaru_matvec(amaru_model *m, double a, double b, const double *x, double *y, char *msg, int msglen) {
+    return guarded(msg, msglen, [&]() {
+        AMARU_REQUIRE(m && x && y, AMARU_ERR_ARG, "null argument");
+        use_device(m);
+        const double sa = m->sysA, sb = m->sysB;
+        const int kind = m->minv_kind;
+        m->sysA = a; m->sysB = b;
+        amaru_combine_matrix(m);
+        const size_t bytes = (size_t)m->ndofs * sizeof(double);
+        CUDA_CHECK(cudaMemcpyAsync(m->d_U, x, bytes, cudaMemcpyHostToDevice, m->stream));
+        amaru_eq_to_nodes(m, m->d_U, m->d_x);
+        amaru_spmv(m, m->d_A, m->d_x, m->d_q, 0);
+        amaru_nodes_to_eq(m, m->d_q, m->d_F, 0);
+        CUDA_CHECK(cudaMemcpyAsync(y, m->d_F, bytes, cudaMemcpyDeviceToHost, m->stream));
+        CUDA_CHECK(cudaStreamSynchronize(m->stream));
+        m->sysA = sa; m->sysB = sb;
+        amaru_combine_matrix(m);
+        (void)kind;
+        return AMARU_OK;
+    });
+}
+
+int amaru_set_device_vectors(amaru_model *m, const double *U, const double *F, char *msg, int msglen) {
+    return guarded(msg, msglen, [&]() {
+        AMARU_REQUIRE(m && U && F, AMARU_ERR_ARG, "null argument");
+        use_device(m);
+        const size_t bytes = (size_t)m->ndofs * sizeof(double);
+        if (!m->d_U0) CUDA_CHECK(cudaMalloc(&m->d_U0, bytes));
+        if (!m->d_F0) CUDA_CHECK(cudaMalloc(&m->d_F0, bytes));
+        CUDA_CHECK(cudaMemcpyAsync(m->d_U0, U, bytes, cudaMemcpyHostToDevice, m->stream));
+        CUDA_CHECK(cudaMemcpyAsync(m->d_F0, F, bytes, cudaMemcpyHostToDevice, m->stream));
+        CUDA_CHECK(cudaStreamSynchronize(m->stream));
+        return AMARU_OK;
+    });
+}
+
+int amaru_newton_iteration_device(amaru_model *m, double cg_rtol, int cg_maxit, int precond, double *phase_ms, int *iters,
+                                  double *relres, char *msg, int msglen) {
+    return guarded(msg, msglen, [&]() {
+        AMARU_REQUIRE(m && m->d_U0 && m->d_F0, AMARU_ERR_ARG, "amaru_newton_iteration_device: call amaru_set_device_vectors first");
+        use_device(m);
+        const size_t bytes = (size_t)m->ndofs * sizeof(double);
+        cudaEvent_t ev[4];
+        for (auto &e : ev) CUDA_CHECK(cudaEventCreate(&e));
+        CUDA_CHECK(cudaEventRecord(ev[0], m->stream));
+        reset_status(m);
+        amaru_launch_assemble(m, 0);                                   // mount_K            (mech-solver.jl:327)
+        amaru_combine_matrix(m);
+        CUDA_CHECK(cudaEventRecord(ev[1], m->stream));
+        CUDA_CHECK(cudaMemcpyAsync(m->d_U, m->d_U0, bytes, cudaMemcpyDeviceToDevice, m->stream));
+        CUDA_CHECK(cudaMemcpyAsync(m->d_F, m->d_F0, bytes, cudaMemcpyDeviceToDevice, m->stream));
+        SolveInfo info;
+        int st = solve_device(m, cg_rtol, cg_maxit, precond, info);    // solve_system!      (:331)
+        CUDA_CHECK(cudaEventRecord(ev[2], m->stream));
+        amaru_state_restore(m);                                        // copyto!(State,Bk)  (:333)
+        const int st2 = update_device(m);                              // update_state!      (:335)
+        CUDA_CHECK(cudaEventRecord(ev[3], m->stream));
+        CUDA_CHECK(cudaEventSynchronize(ev[3]));
+        if (phase_ms) {
+            float t;
+            for (int i = 0; i < 3; i++) {
+                CUDA_CHECK(cudaEventElapsedTime(&t, ev[i], ev[i + 1]));
+                phase_ms[i] = t;
+            }
+            CUDA_CHECK(cudaEventElapsedTime(&t, ev[0], ev[3]));
+            phase_ms[3] = t;
+        }
+        for (auto &e : ev) cudaEventDestroy(e);
+        if (iters) *iters = info.iters;
+        if (relres) *relres = info.relres;
+        const int as = read_status(m);
+        if (as) st = as;
+        if (st == AMARU_OK) st = st2;
+        if (st) throw AmaruError{st, status_text(st)};
+        return AMARU_OK;
+    });
+}
+
+int amaru_time_kernel(amaru_model *m, int kind, int precond, int reps, double *avg_ms, char *msg, int msglen) {
+    return guarded(msg, msglen, [&]() {
+        AMARU_REQUIRE(m && avg_ms && reps > 0, AMARU_ERR_ARG, "bad argument");
+        use_device(m);
+        cudaEvent_t e0, e1;
+        CUDA_CHECK(cudaEventCreate(&e0));
+        CUDA_CHECK(cudaEventCreate(&e1));
+        if (kind >= 3 || kind == 0) amaru_time_cg_kernel(m, kind, precond, 1);   // warm-up
+        CUDA_CHECK(cudaEventRecord(e0, m->stream));
+        if (kind == 1) {
+            for (int i = 0; i < reps; i++) amaru_launch_assemble(m, 0);
+        } else if (kind == 2) {
+            for (int i = 0; i < reps; i++) amaru_launch_update(m, m->d_x, m->d_f, 1);
+        } else {
+            amaru_time_cg_kernel(m, kind, precond, reps);
+        }
+        CUDA_CHECK(cudaEventRecord(e1, m->stream));
+        CUDA_CHECK(cudaEventSynchronize(e1));
+        float t = 0.f;
+        CUDA_CHECK(cudaEventElapsedTime(&t, e0, e1));
+        *avg_ms = (double)t / reps;
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+        return AMARU_OK;
+    });
+}
+
+int amaru_set_profiling(amaru_model *m, int on) {
+    if (!m) return AMARU_ERR_ARG;
+    m->profiling = on != 0;
+    m->prof_spmv_ms = 0.0;
+    m->prof_spmv_n = 0;
+    return AMARU_OK;
+}
+
+int amaru_get_profile(amaru_model *m, double *spmv_ms_total, int64_t *spmv_launches) {
+    if (!m) return AMARU_ERR_ARG;
+    if (spmv_ms_total) *spmv_ms_total = m->prof_spmv_ms;
+    if (spmv_launches) *spmv_launches = m->prof_spmv_n;
+    return AMARU_OK;
+}
+
+}  // extern "C"

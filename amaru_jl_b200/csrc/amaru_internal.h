@@ -1,0 +1,166 @@
+// Internal declarations shared by the translation units of libamaru_b200.so (not part of the ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "../../include/amaru_b200.h"
+
+#define AMARU_MAXNN 20
+#define AMARU_NSTATE 14  // planes: 0-5 sigma, 6-11 eps, 12 epa, 13 dlam (Δλ | Δγ)
+
+// ---- error plumbing -------------------------------------------------------------------------------------
+struct AmaruError {
+    int code;
+    std::string msg;
+};
+#define CUDA_CHECK(call)                                                                          \
+    do {                                                                                          \
+        cudaError_t err__ = (call);                                                               \
+        if (err__ != cudaSuccess)                                                                 \
+            throw AmaruError{AMARU_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(err__)}; \
+    } while (0)
+#define AMARU_REQUIRE(cond, code, text) \
+    do {                                \
+        if (!(cond)) throw AmaruError{(code), (text)}; \
+    } while (0)
+
+// ---- shape tables (host) ---------------------------------------------------------------------------------
+struct ShapeInfo {
+    int id, nn, nd, nip;
+    std::vector<double> nat;    // nn*nd natural coordinates
+    std::vector<double> ips;    // nip*4 (r,s,t,w)
+    std::vector<double> N;      // nip*nn
+    std::vector<double> dNdR;   // nip*nn*nd
+};
+bool amaru_shape_info(int shape_id, ShapeInfo &out);
+
+// ---- host preprocessing (host_prep.cpp) -------------------------------------------------------------------
+struct HostPattern {
+    std::vector<int32_t> rowptr;   // nrows+1   (block rows = nodes 0..nrows-1)
+    std::vector<int32_t> col;      // nblk, ascending inside a row
+    std::vector<int32_t> diag;     // nrows: index of the diagonal block
+};
+// node->element adjacency over all batches (element ids are global across batches)
+void amaru_build_adjacency(int64_t nnodes, int nbatches, const int *nn, const int64_t *nelem,
+                           const int32_t *const *conn, std::vector<int64_t> &adj_ptr, std::vector<int64_t> &adj);
+// greedy colouring: elements sharing a node get different colours; returns number of colours
+int amaru_color_elements(int64_t nnodes, int nbatches, const int *nn, const int64_t *nelem,
+                         const int32_t *const *conn, const std::vector<int64_t> &adj_ptr,
+                         const std::vector<int64_t> &adj, std::vector<int32_t> &color);
+// symbolic block pattern for rows [0,nrows): union of the nodes of all elements touching the row node
+void amaru_build_pattern(int64_t nrows, int nbatches, const int *nn, const int64_t *nelem,
+                         const int32_t *const *conn, const std::vector<int64_t> &adj_ptr,
+                         const std::vector<int64_t> &adj, HostPattern &pat);
+int amaru_host_threads();
+
+// ---- device model ------------------------------------------------------------------------------------------
+struct Batch {
+    int shape = 0, nn = 0, nd = 0, nip = 0;
+    int64_t nelem = 0;
+    int64_t elem_off = 0;          // first element of this batch in the ABI element order
+    int64_t ip_off = 0;            // first IP of this batch in the device state planes
+    std::vector<int64_t> color_off;  // ncolors+1 offsets into the colour-sorted arrays
+    int32_t *d_conn = nullptr;     // [nelem*nn]   colour-sorted, element-major
+    int32_t *d_emat = nullptr;     // [nelem]      material index, colour-sorted
+    int32_t *d_map = nullptr;      // [nelem*nn*nn] destination block of pair (a,b)
+    int64_t *d_perm = nullptr;     // [nelem]      colour-sorted position -> element index inside the batch
+    uint8_t *d_owned = nullptr;    // [nelem]      1 if this rank owns the element (multi-GPU), else nullptr
+    double *d_rho = nullptr;       // [nelem]      density, colour-sorted (mass assembly)
+    double *d_dNdR = nullptr;      // [nip*nn*nd]
+    double *d_N = nullptr;         // [nip*nn]
+    double *d_w = nullptr;         // [nip]
+};
+
+struct CgScalars;  // device-side scalar block (pcg.cu)
+
+struct amaru_model {
+    int device = 0;
+    int ndim = 0, nd = 0, stressmodel = 0;
+    double th = 1.0;
+    int64_t nnodes = 0;        // local nodes (owned + ghost)
+    int64_t nowned = 0;        // rows of the local matrix
+    int64_t ndofs = 0, nu = 0; // ABI vector length / unknown dofs (global numbers)
+    int64_t nelem_total = 0, nip_total = 0;
+    int ncolors = 0;
+    int nmats = 0;
+    cudaStream_t stream = nullptr;
+    int nsm = 148;
+
+    std::vector<Batch> batches;
+    double *d_coords = nullptr;    // [nnodes*3]
+    int32_t *d_eqid = nullptr;     // [nnodes*nd] local dof (node-major) -> ABI eq index
+    uint8_t *d_fixed = nullptr;    // [nnodes*nd] 1 = prescribed
+    int32_t *d_mat_kind = nullptr; // [nmats]
+    double *d_mat_par = nullptr;   // [nmats*8]
+
+    // block-CSR matrix, rows = owned nodes, columns = local nodes
+    int64_t nblk = 0;
+    int32_t *d_rowptr = nullptr, *d_col = nullptr, *d_diag = nullptr;
+    double *d_K = nullptr;         // [nblk*nd*nd]
+    double *d_M = nullptr;         // mass, same pattern (next tier)
+    double *d_A = nullptr;         // a*K+b*M when a system matrix is set, else == d_K
+    double sysA = 1.0, sysB = 0.0;
+    double *d_Minv = nullptr;      // block-Jacobi inverses [nowned*nd*nd] or Jacobi [nowned*nd]
+    int minv_kind = -1;            // which preconditioner d_Minv currently holds (-1 = stale)
+
+    // IP state planes [AMARU_NSTATE][nip_total] and the converged backup
+    double *d_state = nullptr, *d_statebk = nullptr;
+
+    // work vectors, node-major, length nnodes*nd
+    double *d_x = nullptr, *d_r = nullptr, *d_z = nullptr, *d_p = nullptr, *d_q = nullptr, *d_b = nullptr;
+    double *d_f = nullptr;         // internal forces accumulator
+    double *d_io = nullptr;        // ABI-order staging buffer, length max(ndofs, 6*nip_total)
+    double *d_U = nullptr, *d_F = nullptr;  // device-resident ABI-order vectors
+    double *d_U0 = nullptr, *d_F0 = nullptr;  // inputs of amaru_newton_iteration_device (measurement hook)
+    int64_t io_len = 0;
+
+    // reductions / flags
+    double *d_partial = nullptr;   // per-block partial sums
+    CgScalars *d_scal = nullptr;
+    int *d_status = nullptr;       // element-kernel failure flag
+    int *h_pinned = nullptr;       // pinned host mirror for small reads
+    int grid_rows = 0;             // persistent grid used by the row kernels
+
+    // multi-GPU
+    int rank = 0, nranks = 1;
+    void *comm = nullptr;          // HaloComm* (halo.cu)
+
+    // bookkeeping
+    int64_t launches = 0;
+    bool profiling = false;
+    double prof_spmv_ms = 0.0;
+    int64_t prof_spmv_n = 0;
+    std::vector<cudaEvent_t> ev_pool;
+
+    // host copies kept for get_csr
+    std::vector<int32_t> h_rowptr, h_col, h_eqid;
+};
+
+// ---- kernels' host entry points (one per .cu) -----------------------------------------------------------------
+void amaru_build_map(amaru_model *m, Batch &b);                     // assemble.cu
+void amaru_launch_assemble(amaru_model *m, int what /*0 K, 1 M*/);   // assemble.cu
+void amaru_launch_update(amaru_model *m, const double *d_dU_nodes, double *d_f_nodes, int mode);  // update.cu
+void amaru_state_permute(amaru_model *m, double *d_io, int plane0, int ncomp, bool to_device);    // update.cu
+
+struct SolveInfo {
+    int iters = 0;
+    double relres = 0.0;
+    double maxabs = 0.0;
+    bool converged = false;
+};
+void amaru_pcg_setup(amaru_model *m);                                // pcg.cu (allocations)
+void amaru_pcg_solve(amaru_model *m, double rtol, int maxit, int precond, SolveInfo &info);  // pcg.cu
+void amaru_spmv(amaru_model *m, const double *A, const double *x, double *y, int mask_mode);  // pcg.cu
+void amaru_eq_to_nodes(amaru_model *m, const double *d_eq, double *d_nodes);                  // pcg.cu
+void amaru_nodes_to_eq(amaru_model *m, const double *d_nodes, double *d_eq, int which /*0 all,1 free,2 fixed*/);
+void amaru_combine_matrix(amaru_model *m);                            // pcg.cu: d_A = a*K + b*M
+int amaru_check_nan(amaru_model *m, const double *d_v, int64_t n);    // pcg.cu
+void amaru_zero_free(amaru_model *m, double *x);                     // pcg.cu
+void amaru_time_cg_kernel(amaru_model *m, int kind, int precond, int reps);  // pcg.cu
+
+// halo exchange (halo.cu) — no-ops for nranks == 1
+void amaru_halo_exchange(amaru_model *m, double *d_v);
+void amaru_allreduce_sum(amaru_model *m, double *d_vals, int n);
+void amaru_allreduce_max_int(amaru_model *m, int *d_val);

@@ -1,0 +1,254 @@
+"""ctypes binding of libamaru_b200.so (include/amaru_b200.h) — the same calls the Julia glue makes with ``ccall``.
+
+There is no CPU fallback: if the shared library is missing, or no CUDA device is visible, every compute entry point
+raises.  Nothing here imports torch; device memory is owned by the library.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from .model import AmaruError
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libamaru_b200.so")
+
+OK = 0
+FAIL_MATERIAL, FAIL_NAN, FAIL_SINGULAR, FAIL_NEG_JACOBIAN, FAIL_CG_NOCONV, FAIL_TANGENT = 1, 2, 3, 4, 5, 6
+ERR_ARG, ERR_CUDA, ERR_NO_DEVICE, ERR_UNSUPPORTED, ERR_COMM = -1, -2, -3, -4, -5
+PRECOND_JACOBI, PRECOND_BLOCK_JACOBI = 0, 1
+PRECOND = {"jacobi": PRECOND_JACOBI, "block-jacobi": PRECOND_BLOCK_JACOBI, "block_jacobi": PRECOND_BLOCK_JACOBI,
+           "bjacobi": PRECOND_BLOCK_JACOBI}
+
+_dp = C.POINTER(C.c_double)
+_i32p = C.POINTER(C.c_int32)
+_i64p = C.POINTER(C.c_int64)
+_u8p = C.POINTER(C.c_uint8)
+_vp = C.c_void_p
+
+# every symbol include/amaru_b200.h declares: name -> (restype, argtypes)
+SYMBOLS = {
+    "amaru_device_count": (C.c_int, []),
+    "amaru_version": (C.c_char_p, []),
+    "amaru_create": (C.c_int, [C.c_int, C.c_int, C.c_double, C.c_int64, _dp, C.c_int, _i32p, _i64p, _i32p, _i32p,
+                               C.c_int, _i32p, _dp, _i32p, C.c_int64, C.c_int64, C.c_int, C.POINTER(_vp), C.c_char_p,
+                               C.c_int]),
+    "amaru_create_partitioned": (C.c_int, [C.c_int, C.c_int, C.c_double, C.c_int64, C.c_int64, _dp, _i64p, _i32p,
+                                           C.c_int, _i32p, _i64p, _i32p, _i32p, _u8p, C.c_int, _i32p, _dp, _i32p, _u8p,
+                                           C.c_int64, C.c_int64, C.c_int, C.c_int, _vp, C.c_int, C.POINTER(_vp),
+                                           C.c_char_p, C.c_int]),
+    "amaru_nccl_unique_id": (C.c_int, [_vp, C.c_char_p, C.c_int]),
+    "amaru_destroy": (C.c_int, [_vp]),
+    "amaru_nip_total": (C.c_int64, [_vp]),
+    "amaru_nnz": (C.c_int64, [_vp]),
+    "amaru_nblocks": (C.c_int64, [_vp]),
+    "amaru_ncolors": (C.c_int, [_vp]),
+    "amaru_set_state": (C.c_int, [_vp, _dp, _dp, _dp, _dp, C.c_char_p, C.c_int]),
+    "amaru_get_state": (C.c_int, [_vp, _dp, _dp, _dp, _dp, C.c_char_p, C.c_int]),
+    "amaru_state_backup": (C.c_int, [_vp]),
+    "amaru_state_restore": (C.c_int, [_vp]),
+    "amaru_assemble_K": (C.c_int, [_vp, C.c_char_p, C.c_int]),
+    "amaru_get_csr": (C.c_int, [_vp, _i64p, _i32p, _dp, C.c_char_p, C.c_int]),
+    "amaru_solve": (C.c_int, [_vp, _dp, _dp, C.c_double, C.c_int, C.c_int, C.POINTER(C.c_int), _dp, C.c_char_p,
+                              C.c_int]),
+    "amaru_update_state": (C.c_int, [_vp, _dp, _dp, C.c_char_p, C.c_int]),
+    "amaru_internal_forces": (C.c_int, [_vp, _dp, C.c_char_p, C.c_int]),
+    "amaru_assemble_M": (C.c_int, [_vp, _dp, C.c_char_p, C.c_int]),
+    "amaru_set_system_matrix": (C.c_int, [_vp, C.c_double, C.c_double, C.c_char_p, C.c_int]),
+    "amaru_matvec": (C.c_int, [_vp, C.c_double, C.c_double, _dp, _dp, C.c_char_p, C.c_int]),
+    "amaru_newton_iteration_device": (C.c_int, [_vp, C.c_double, C.c_int, C.c_int, _dp, C.POINTER(C.c_int), _dp,
+                                                C.c_char_p, C.c_int]),
+    "amaru_set_device_vectors": (C.c_int, [_vp, _dp, _dp, C.c_char_p, C.c_int]),
+    "amaru_time_kernel": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _dp, C.c_char_p, C.c_int]),
+    "amaru_set_profiling": (C.c_int, [_vp, C.c_int]),
+    "amaru_get_profile": (C.c_int, [_vp, _dp, _i64p]),
+    "amaru_launch_count": (C.c_int64, [_vp]),
+}
+
+_LIB = None
+
+
+def load():
+    """Load libamaru_b200.so; fails loudly if it was not built (python __graft_entry__.py build)."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise AmaruError(f"{LIB_PATH} is missing: build it with `make -C amaru_jl_b200/csrc` "
+                             "(there is no CPU fallback for the mechanical hot path)")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _LIB = lib
+    return _LIB
+
+
+def device_count():
+    return load().amaru_device_count()
+
+
+def _d(a):
+    return a.ctypes.data_as(_dp) if a is not None else None
+
+
+class AmaruStatus(AmaruError):
+    """A non-zero status from the library: ``code > 0`` = ReturnStatus failure, ``code < 0`` = usage / CUDA error."""
+
+    def __init__(self, code, msg):
+        super().__init__(f"[{code}] {msg}")
+        self.code, self.message = code, msg
+
+
+class DeviceModel:
+    """One stage's device handle (``amaru_create`` ... ``amaru_destroy``)."""
+
+    def __init__(self, flat: dict, eqid: np.ndarray, ndofs: int, nu: int, device: int = 0):
+        self.lib = load()
+        self._msg = C.create_string_buffer(512)
+        self.ndofs, self.nu = int(ndofs), int(nu)
+        coords = np.ascontiguousarray(flat["coords"], dtype=np.float64)
+        bshape = np.ascontiguousarray(flat["batch_shape"], dtype=np.int32)
+        bnelem = np.ascontiguousarray(flat["batch_nelem"], dtype=np.int64)
+        conn = np.ascontiguousarray(flat["conn"], dtype=np.int32).reshape(-1)
+        emat = np.ascontiguousarray(flat["elem_mat"], dtype=np.int32)
+        mkind = np.ascontiguousarray(flat["mat_kind"], dtype=np.int32)
+        mpar = np.ascontiguousarray(flat["mat_params"], dtype=np.float64).reshape(-1)
+        eq = np.ascontiguousarray(eqid, dtype=np.int32).reshape(-1)
+        h = _vp()
+        st = self.lib.amaru_create(int(flat["ndim"]), int(flat["stressmodel"]), float(flat["thickness"]),
+                                   coords.shape[0], _d(coords), len(bshape), bshape.ctypes.data_as(_i32p),
+                                   bnelem.ctypes.data_as(_i64p), conn.ctypes.data_as(_i32p),
+                                   emat.ctypes.data_as(_i32p), len(mkind), mkind.ctypes.data_as(_i32p), _d(mpar),
+                                   eq.ctypes.data_as(_i32p), self.ndofs, self.nu, int(device), C.byref(h), self._msg,
+                                   len(self._msg))
+        if st != OK:
+            raise AmaruStatus(st, self._msg.value.decode(errors="replace"))
+        self.h = h
+        self.nip_total = self.lib.amaru_nip_total(h)
+
+    # -- helpers
+    def _check(self, st):
+        if st != OK:
+            raise AmaruStatus(st, self._msg.value.decode(errors="replace"))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.amaru_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def nnz(self):
+        return self.lib.amaru_nnz(self.h)
+
+    @property
+    def nblocks(self):
+        return self.lib.amaru_nblocks(self.h)
+
+    @property
+    def ncolors(self):
+        return self.lib.amaru_ncolors(self.h)
+
+    @property
+    def launches(self):
+        return self.lib.amaru_launch_count(self.h)
+
+    # -- state
+    def set_state(self, sigma=None, eps=None, epa=None, dlam=None):
+        arrs = [None if a is None else np.ascontiguousarray(a, dtype=np.float64) for a in (sigma, eps, epa, dlam)]
+        self._check(self.lib.amaru_set_state(self.h, *[_d(a) for a in arrs], self._msg, len(self._msg)))
+
+    def get_state(self):
+        n = self.nip_total
+        sig, eps, epa, dl = np.empty((n, 6)), np.empty((n, 6)), np.empty(n), np.empty(n)
+        self._check(self.lib.amaru_get_state(self.h, _d(sig), _d(eps), _d(epa), _d(dl), self._msg, len(self._msg)))
+        return dict(sigma=sig, eps=eps, epa=epa, dlam=dl)
+
+    def state_backup(self):
+        self._check(self.lib.amaru_state_backup(self.h))
+
+    def state_restore(self):
+        self._check(self.lib.amaru_state_restore(self.h))
+
+    # -- the three hot calls
+    def assemble_K(self):
+        self._check(self.lib.amaru_assemble_K(self.h, self._msg, len(self._msg)))
+
+    def solve(self, U, F, cg_rtol=1e-10, cg_maxit=100000, precond=PRECOND_BLOCK_JACOBI):
+        """In place on U[:nu] and F[nu:] like solve_system!; returns (iters, relres)."""
+        assert U.dtype == np.float64 and F.dtype == np.float64 and U.flags.c_contiguous and F.flags.c_contiguous
+        it, rr = C.c_int(0), C.c_double(0)
+        self._check(self.lib.amaru_solve(self.h, _d(U), _d(F), float(cg_rtol), int(cg_maxit), int(precond),
+                                         C.byref(it), C.byref(rr), self._msg, len(self._msg)))
+        return it.value, rr.value
+
+    def update_state(self, dU, dFin=None):
+        dU = np.ascontiguousarray(dU, dtype=np.float64)
+        if dFin is None:
+            dFin = np.empty(self.ndofs)
+        self._check(self.lib.amaru_update_state(self.h, _d(dU), _d(dFin), self._msg, len(self._msg)))
+        return dFin
+
+    def internal_forces(self):
+        F = np.empty(self.ndofs)
+        self._check(self.lib.amaru_internal_forces(self.h, _d(F), self._msg, len(self._msg)))
+        return F
+
+    def get_csr(self, values=True):
+        nnz = self.nnz
+        rowptr = np.empty(self.ndofs + 1, dtype=np.int64)
+        col = np.empty(nnz, dtype=np.int32)
+        val = np.empty(nnz) if values else None
+        self._check(self.lib.amaru_get_csr(self.h, rowptr.ctypes.data_as(_i64p), col.ctypes.data_as(_i32p), _d(val),
+                                           self._msg, len(self._msg)))
+        return rowptr, col, val
+
+    # -- next tier (Newmark)
+    def assemble_M(self, rho):
+        rho = np.ascontiguousarray(rho, dtype=np.float64)
+        self._check(self.lib.amaru_assemble_M(self.h, _d(rho), self._msg, len(self._msg)))
+
+    def set_system_matrix(self, a, b):
+        self._check(self.lib.amaru_set_system_matrix(self.h, float(a), float(b), self._msg, len(self._msg)))
+
+    def matvec(self, a, b, x):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        y = np.empty(self.ndofs)
+        self._check(self.lib.amaru_matvec(self.h, float(a), float(b), _d(x), _d(y), self._msg, len(self._msg)))
+        return y
+
+    # -- measurement hooks
+    def set_device_vectors(self, U, F):
+        U = np.ascontiguousarray(U, dtype=np.float64)
+        F = np.ascontiguousarray(F, dtype=np.float64)
+        self._check(self.lib.amaru_set_device_vectors(self.h, _d(U), _d(F), self._msg, len(self._msg)))
+
+    def newton_iteration_device(self, cg_rtol=1e-10, cg_maxit=100000, precond=PRECOND_BLOCK_JACOBI):
+        ms = np.zeros(4)
+        it, rr = C.c_int(0), C.c_double(0)
+        self._check(self.lib.amaru_newton_iteration_device(self.h, float(cg_rtol), int(cg_maxit), int(precond), _d(ms),
+                                                           C.byref(it), C.byref(rr), self._msg, len(self._msg)))
+        return dict(assemble_ms=ms[0], solve_ms=ms[1], update_ms=ms[2], total_ms=ms[3], cg_iters=it.value,
+                    relres=rr.value)
+
+    def time_kernel(self, kind, reps=20, precond=PRECOND_BLOCK_JACOBI):
+        t = C.c_double(0)
+        self._check(self.lib.amaru_time_kernel(self.h, int(kind), int(precond), int(reps), C.byref(t), self._msg,
+                                               len(self._msg)))
+        return t.value
+
+    def set_profiling(self, on=True):
+        self.lib.amaru_set_profiling(self.h, 1 if on else 0)
+
+    def get_profile(self):
+        t, n = C.c_double(0), C.c_int64(0)
+        self.lib.amaru_get_profile(self.h, C.byref(t), C.byref(n))
+        return t.value, n.value

@@ -173,6 +173,10 @@ int amaru_set_device_vectors(amaru_model *m, const double *U, const double *F, c
 /* time `reps` launches of one kernel class on the model's stream (CUDA events); kind: 0 SpMV, 1 assemble,
  * 2 update_state, 3 fused CG vector update, 4 p-update. Returns average ms per launch. */
 int amaru_time_kernel(amaru_model *m, int kind, int precond, int reps, double *avg_ms, char *msg, int msglen);
+/* When on, amaru_solve brackets every CG SpMV launch with CUDA events on the model's stream; amaru_get_profile
+ * returns the summed duration (ms) and the number of SpMV launches since profiling was switched on. */
+int amaru_set_profiling(amaru_model *m, int on);
+int amaru_get_profile(amaru_model *m, double *spmv_ms_total, int64_t *spmv_launches);
 /* number of kernels launched by this handle since creation (the bench's gpu_launches claim) */
 int64_t amaru_launch_count(const amaru_model *m);
 

@@ -1,0 +1,310 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle on the same inputs.  Needs a B200: -m gpu.
+
+Tolerances are BASELINE.json's: CSR pattern and dof numbering exact; K, f_int and IP stresses within 1e-12 relative
+(max-norm); displacements from the PCG within 1e-8 relative of the direct solve.
+"""
+import numpy as np
+import pytest
+
+from amaru_jl_b200 import (Block, BodyC, DruckerPrager, FEModel, LinearElastic, MechAnalysis, MechContext, MechSolid,
+                           Mesh, NodeBC, SurfaceBC, VonMises, addstage, solve)
+from amaru_jl_b200 import lib as L
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+MATS = {
+    "le": (LinearElastic, dict(E=100.0, nu=0.2)),
+    "vm": (VonMises, dict(E=210e6, nu=0.3, fy=240e3, H=1e6)),
+    "vm0": (VonMises, dict(E=210e6, nu=0.3, fy=240e3, H=0.0)),
+    "dp": (DruckerPrager, dict(E=100.0, nu=0.25, alpha=0.05, kappa=0.1, H=0.0)),
+}
+
+
+def make_model(shape, n, mat="le", jitter=0.0, seed=0, mixed=False):
+    if shape in ("QUAD4", "QUAD8"):
+        mesh = Mesh(Block([[0, 0], [2, 1]], nx=2 * n, ny=n, cellshape=shape, tag="solids"))
+    else:
+        mesh = Mesh(Block([[0, 0, 0], [1, 1.5, 2]], nx=n, ny=n, nz=n + 1, cellshape=shape, tag="solids"))
+    if jitter:
+        rng = np.random.default_rng(seed)
+        c = mesh.coords
+        lo, hi = c.min(0), c.max(0)
+        interior = np.all((c > lo + 1e-9) | (hi - lo == 0), axis=1) & np.all((c < hi - 1e-9) | (hi - lo == 0), axis=1)
+        h = (hi - lo) / (2 * n + 2)
+        c[interior] += rng.uniform(-jitter, jitter, (interior.sum(), 3)) * h
+        if mesh.ndim == 2:
+            c[:, 2] = 0.0
+        mesh.coords[...] = np.round(c, 8)
+    mty, par = MATS[mat]
+    binds = [("solids", MechSolid, mty, par)]
+    if mixed:   # second material on the upper half: two material ids in one batch
+        binds.append(("y>=0.4" if mesh.ndim == 2 else "z>=0.9", MechSolid, LinearElastic, dict(E=50.0, nu=0.3)))
+    thickness = 0.7 if mesh.ndim == 2 else 1.0
+    return FEModel(mesh, binds, MechContext(), thickness=thickness)
+
+
+def clamp_bcs(model):
+    if model.ndim == 2:
+        return [("x==0", NodeBC(ux=0, uy=0)), ("x==2", NodeBC(uy=-0.01))]
+    return [("z==0", NodeBC(ux=0, uy=0, uz=0)), ("z==2", NodeBC(uz=-0.02, ux=0.003))]
+
+
+def pair(model, bcs):
+    eqid, nu, setup = model.configure_dofs(bcs)
+    om = O.OracleModel(model.flatten(), eqid, eqid.size, nu)
+    dm = L.DeviceModel(model.flatten(), eqid, eqid.size, nu)
+    return om, dm, eqid, nu, setup
+
+
+def rel(a, b):
+    d = np.abs(b).max()
+    return np.abs(a - b).max() / (d if d > 0 else 1.0)
+
+
+def check_K(om, dm, tol=1e-12):
+    dm.assemble_K()
+    rp, ci, val = dm.get_csr()
+    st, K = om.mount_K(filter_eps=False)
+    assert st == 0
+    K = K.tocsr()
+    K.sort_indices()
+    srp, sci = om.symbolic_csr()
+    assert np.array_equal(rp, srp) and np.array_equal(ci, sci), "symbolic CSR pattern differs"
+    assert np.array_equal(K.indptr, rp) and np.array_equal(K.indices, ci)
+    assert rel(val, K.data) < tol
+    # the reference's stored pattern (|v| < eps dropped, mech-solver.jl:90) is a subset whose complement is ~0
+    st, Kf = om.mount_K(filter_eps=True)
+    Kf = Kf.tocsr()
+    assert Kf.nnz <= K.nnz
+    return K
+
+
+SHAPES = [("QUAD4", 3), ("QUAD8", 3), ("HEX8", 3), ("HEX20", 2), ("TET10", 2)]
+
+
+@pytest.mark.parametrize("shape,n", SHAPES)
+def test_K_pattern_and_values_elastic(shape, n):
+    model = make_model(shape, n, "le", jitter=0.2, mixed=True)
+    om, dm, *_ = pair(model, clamp_bcs(model))
+    check_K(om, dm)
+    dm.close()
+
+
+@pytest.mark.parametrize("shape,n", SHAPES)
+@pytest.mark.parametrize("mat", ["le", "vm", "vm0", "dp"])
+def test_update_state_and_tangent(shape, n, mat):
+    """update_state! parity (f_int, sigma, eps, epa, dlam), then mount_K on the updated (trial) state."""
+    model = make_model(shape, n, mat, jitter=0.15, seed=1)
+    om, dm, eqid, nu, _ = pair(model, clamp_bcs(model))
+    rng = np.random.default_rng(2)
+    E = MATS[mat][1]["E"]
+    scale = {"le": 1e-3, "vm": 4e-3, "vm0": 4e-3, "dp": 5e-3}[mat]
+    for step in range(3):                                   # later steps start from a plastic, non-zero state
+        dU = rng.uniform(-1, 1, eqid.size) * scale * (step + 1)
+        dFo, st = om.update_state(dU)
+        assert st == 0
+        dF = dm.update_state(dU)
+        s = dm.get_state()
+        if mat != "le":
+            assert (om.dlam > 0).sum() > 0, "test must exercise the plastic branch"
+        assert rel(dF, dFo) < 1e-12
+        assert rel(s["sigma"], om.sig) < 1e-12
+        assert rel(s["eps"], om.eps) < 1e-12
+        assert rel(s["epa"], om.epa) < 1e-12
+        assert rel(s["dlam"], om.dlam) < 1e-11
+        assert np.array_equal(s["dlam"] > 0, om.dlam > 0)
+        check_K(om, dm, tol=1e-11 if mat != "le" else 1e-12)
+        assert rel(dm.internal_forces(), om.internal_forces()) < 1e-12
+    dm.close()
+
+
+def test_dp_apex_branch():
+    """Hydrostatic tension drives Drucker-Prager to the apex return (drucker-prager.jl:135-139) on the second step
+    (the cone/apex switch uses the previous Δγ, :130)."""
+    model = make_model("HEX8", 2, "dp")
+    om, dm, eqid, nu, _ = pair(model, clamp_bcs(model))
+    X = model.coords
+    U = np.zeros(eqid.size)
+    for k, (amp, sh) in enumerate(((0.02, 0.01), (0.05, 0.0005))):
+        D = amp * X[:, :3].copy()                           # dilation + a little shear (keeps J2tr well conditioned)
+        D[:, 0] += sh * X[:, 1]
+        U[eqid.reshape(-1)] = D.reshape(-1)
+        dFo, st = om.update_state(U)
+        dF = dm.update_state(U)
+        s = dm.get_state()
+        assert st == 0 and rel(dF, dFo) < 1e-12 and rel(s["sigma"], om.sig) < 1e-12 and rel(s["dlam"], om.dlam) < 1e-12
+    j2 = np.array([O.J2(x) for x in om.sig])
+    assert (j2 < 1e-20).any(), "apex return not reached"
+    check_K(om, dm, tol=1e-11)
+    dm.close()
+
+
+@pytest.mark.parametrize("shape,n", [("QUAD8", 4), ("HEX8", 4), ("HEX20", 3), ("TET10", 3)])
+@pytest.mark.parametrize("precond", ["jacobi", "block-jacobi"])
+def test_solve_matches_direct(shape, n, precond):
+    model = make_model(shape, n, "le", jitter=0.1)
+    bcs = clamp_bcs(model) + [("z==2" if model.ndim == 3 else "y==1", SurfaceBC(**({"tz": -3.0} if model.ndim == 3 else {"ty": -3.0})))]
+    om, dm, eqid, nu, setup = pair(model, bcs)
+    Uex, Fex = model.get_bc_vals(eqid, setup)
+    st, K = om.mount_K()
+    dm.assemble_K()
+    U, F = Uex.copy(), Fex.copy()
+    iters, rr = dm.solve(U, F, cg_rtol=1e-12, precond=L.PRECOND[precond])
+    Uo, Fo = Uex.copy(), Fex.copy()
+    ok, _ = O.solve_system(K, Uo, Fo, nu)
+    assert ok and iters > 0 and rr <= 1e-12
+    assert rel(U, Uo) < 1e-8                                 # displacements incl. untouched prescribed part
+    assert np.array_equal(U[nu:], Uex[nu:])                  # solve_system! leaves U2 alone (solver.jl:74)
+    assert np.array_equal(F[:nu], Fex[:nu])                  # ... and F1 (solver.jl:75)
+    assert rel(F[nu:], Fo[nu:]) < 1e-8                       # reactions
+    dm.close()
+
+
+def test_state_roundtrip_backup_restore():
+    model = make_model("HEX20", 2, "vm")
+    om, dm, eqid, *_ = pair(model, clamp_bcs(model))
+    rng = np.random.default_rng(3)
+    n = dm.nip_total
+    sig, eps, epa, dl = rng.normal(size=(n, 6)), rng.normal(size=(n, 6)), rng.uniform(size=n), rng.uniform(size=n)
+    dm.set_state(sig, eps, epa, dl)
+    s = dm.get_state()
+    assert np.array_equal(s["sigma"], sig) and np.array_equal(s["eps"], eps)
+    assert np.array_equal(s["epa"], epa) and np.array_equal(s["dlam"], dl)
+    dm.state_backup()
+    dm.update_state(rng.uniform(-1, 1, eqid.size) * 1e-3)
+    assert not np.array_equal(dm.get_state()["sigma"], sig)
+    dm.state_restore()
+    assert np.array_equal(dm.get_state()["sigma"], sig)
+    dm.close()
+
+
+def test_assembly_is_deterministic():
+    model = make_model("HEX20", 3, "vm0", jitter=0.1)
+    om, dm, eqid, *_ = pair(model, clamp_bcs(model))
+    dm.update_state(np.random.default_rng(5).uniform(-1, 1, eqid.size) * 5e-3)
+    dm.assemble_K()
+    a = dm.get_csr()[2].copy()
+    f1 = dm.internal_forces().copy()
+    for _ in range(3):
+        dm.assemble_K()
+        assert np.array_equal(dm.get_csr()[2], a)            # bitwise
+        assert np.array_equal(dm.internal_forces(), f1)
+    dm.close()
+
+
+def test_failure_statuses():
+    # negative Jacobian (mech-solid.jl:150): swap two nodes of one element
+    model = make_model("HEX8", 2, "le")
+    model.conn[0, [0, 1]] = model.conn[0, [1, 0]]
+    eqid, nu, _ = model.configure_dofs(clamp_bcs(model))
+    dm = L.DeviceModel(model.flatten(), eqid, eqid.size, nu)
+    with pytest.raises(L.AmaruStatus) as e:
+        dm.assemble_K()
+    assert e.value.code == L.FAIL_NEG_JACOBIAN
+    dm.close()
+    # no essential BCs: K11 singular -> the CG cannot converge / blows up, reported as a ReturnStatus failure
+    model = make_model("HEX8", 2, "le")
+    eqid, nu, setup = model.configure_dofs([("z==2", NodeBC(fz=1.0))])
+    dm = L.DeviceModel(model.flatten(), eqid, eqid.size, nu)
+    dm.assemble_K()
+    U, F = model.get_bc_vals(eqid, setup)
+    with pytest.raises(L.AmaruStatus) as e:
+        dm.solve(U, F, cg_rtol=1e-12, cg_maxit=300)
+    assert e.value.code in (L.FAIL_CG_NOCONV, L.FAIL_SINGULAR)
+    dm.close()
+    # unsupported shape id / material kind are refused (no CPU fallback)
+    flat = model.flatten()
+    flat["mat_kind"] = np.array([99], dtype=np.int32)
+    with pytest.raises(L.AmaruStatus) as e:
+        L.DeviceModel(flat, eqid, eqid.size, nu)
+    assert e.value.code == L.ERR_UNSUPPORTED
+
+
+# ------------------------------------------------------------------------------------------ whole solve! through the driver
+def drive_both(model_fn, bcs_list, **kw):
+    """Run the product solve() and the oracle's mech_stage_solver on the same stages; return both end states."""
+    model = model_fn()
+    ana = MechAnalysis(model)
+    for bcs, nincs in bcs_list:
+        addstage(ana, bcs, nincs=nincs)
+    status = solve(ana, cg_rtol=1e-12, **kw)
+    ref = model_fn()
+    om = None
+    Uacc = np.zeros((ref.nnodes, ref.ndim))
+    for bcs, nincs in bcs_list:
+        eqid, nu, setup = ref.configure_dofs(bcs)
+        Uex, Fex = ref.get_bc_vals(eqid, setup)
+        if om is None:
+            om = O.OracleModel(ref.flatten(), eqid, eqid.size, nu)
+        om.eqid, om.nu = np.ascontiguousarray(eqid), nu
+        r = O.mech_stage_solver(om, Uex, Fex, nincs=nincs, **kw)
+        Uacc += r["U"][eqid]
+    return status, model, ana, r, Uacc, om
+
+
+def test_solve_known_answers_quad4_hex8():
+    # reference test/mech/elem/elastic-quad4.jl and elastic-hex8.jl (nodal load case), through the GPU path
+    mesh = Mesh(Block([[0, 0], [1, 1]], nx=1, ny=1, cellshape="QUAD4", tag="solid"))
+    model = FEModel(mesh, [("solid", MechSolid, LinearElastic, dict(E=1.0, nu=0.25))], MechContext(stressmodel="planestrain"))
+    ana = MechAnalysis(model)
+    addstage(ana, [("x==0.", SurfaceBC(ux=0.)), ("y==0.", SurfaceBC(uy=0)), ("y==1.", SurfaceBC(ty=-1.))], nincs=1)
+    assert solve(ana).success
+    assert np.abs(model.U - np.array([[0, 0], [0.3125, 0], [0, -0.9375], [0.3125, -0.9375]])).max() < 1e-5
+    mesh = Mesh(Block([[0, 0, 0], [1, 1, 1]], nx=1, ny=1, nz=1, cellshape="HEX8", tag="solid"))
+    base = [("x==0 && y==0 && z==0", NodeBC(ux=0, uy=0)), ("x==1 && y==0 && z==0", NodeBC(uy=0)),
+            ("x==0 && y==1 && z==0", NodeBC(ux=0)), ("z==0", NodeBC(uz=0))]
+    for extra, uz in [(("z==1", NodeBC(fz=1)), [0, 0, 0, 0, 4.0, 4.0, 4.0, 4.0]),
+                      (("x==1", SurfaceBC(tx="3*z")), [0, 0, 0, 0, 1.51044, -2.4501, 1.4499, -2.31023]),
+                      (("x>=0", BodyC(wz=-1)), [0, 0, 0, 0, -0.5, -0.5, -0.5, -0.5])]:
+        model = FEModel(mesh, [("solid", MechSolid, LinearElastic, dict(E=1.0, nu=0.3))], MechContext())
+        ana = MechAnalysis(model)
+        addstage(ana, base + [extra], nouts=1)
+        assert solve(ana).success
+        assert np.abs(model.U[:, 2] - np.array(uz)).max() < 1e-5
+
+
+def test_solve_config1_quad8_cantilever():
+    """BASELINE config 1: QUAD8 20x10 plane-strain cantilever, E=200e6 nu=0.2, one load step."""
+    def mk():
+        mesh = Mesh(Block([[0, 0], [3, 0.4]], nx=20, ny=10, cellshape="QUAD8", tag="solids"))
+        return FEModel(mesh, [("solids", MechSolid, LinearElastic, dict(E=200e6, nu=0.2))], MechContext(stressmodel="planestrain"))
+    bcs = [("x==0", NodeBC(ux=0, uy=0)), ("y==0.4", SurfaceBC(ty="-0.1*x"))]
+    status, model, ana, r, Uacc, om = drive_both(mk, [(bcs, 1)])
+    assert status.success and r["success"]
+    assert model.nnodes == 661
+    assert rel(model.U, Uacc) < 1e-8
+    assert rel(model.state["sigma"], om.sig) < 1e-7
+
+
+def test_solve_vm_cantilever_fixed_increments():
+    """reference test/mech/mat/vm-3d.jl scenario with fixed increments (autoinc trajectories amplify solver noise):
+    same increments, Newton iterations and end state as the oracle driver with the direct solver."""
+    th = 0.05
+
+    def mk():
+        mesh = Mesh(Block([[0, 0, -0.05], [0.05, 1.0, 0.05]], nx=1, ny=30, nz=2, cellshape="HEX20"))
+        return FEModel(mesh, [("bulks", MechSolid, VonMises, dict(E=210e6, nu=0.3, fy=240e3, H=0))], MechContext())
+    bcs = [("y==0", NodeBC(uy=0)), ("y==0 && z==0", NodeBC(uz=0)), (f"x=={th/2} && y==0 && z==0", NodeBC(ux=0)),
+           (f"x=={th/2} && y==1 && z==0", NodeBC(uz=-0.02))]
+    status, model, ana, r, Uacc, om = drive_both(mk, [(bcs, 10)], maxits=5, tol=1e-2, rtol=1e-2)
+    assert status.success == r["success"]
+    assert len(ana.stats) == r["its"]
+    assert rel(model.U, Uacc) < 1e-7
+    assert rel(model.state["sigma"], om.sig) < 1e-6
+    assert (model.state["epa"] > 0).sum() == (om.epa > 0).sum() > 0
+
+
+def test_solve_dp_two_stages_autoinc():
+    """reference test/mech/mat/dp.jl: load then unload, IP state carried across stages, autoinc; `.success`."""
+    def mk():
+        mesh = Mesh(Block([[0, 0, 0], [1, 1, 0.5]], nx=2, ny=2, nz=2, tag="solids"))
+        return FEModel(mesh, [("solids", MechSolid, DruckerPrager, dict(E=100., nu=0.25, alpha=0.05, kappa=0.1))], MechContext())
+    b1 = [("z==0.0", NodeBC(ux=0, uy=0, uz=0)), ("z==0.5", NodeBC(uz=-0.033)),
+          ("x==0 || x==1.0", NodeBC(ux=0, uy=0)), ("y==0 || y==1.0", NodeBC(ux=0, uy=0))]
+    b2 = list(b1)
+    b2[1] = ("z==0.5", NodeBC(uz=+0.008))
+    status, model, ana, r, Uacc, om = drive_both(mk, [(b1, 10), (b2, 10)], tol=1e-2, autoinc=True)
+    assert status.success and r["success"]
+    assert rel(model.U, Uacc) < 1e-6
+    assert rel(model.state["epa"], om.epa) < 1e-6
