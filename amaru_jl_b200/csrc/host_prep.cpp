@@ -270,3 +270,37 @@ void amaru_build_pattern(int64_t nrows, int nbatches, const int *nn, const int64
         }
     });
 }
+
+// ---------------------------------------------------------------------------------------------- CPU-only probe
+// Runs the host preprocessing alone (no CUDA calls) so that the host logic can be tested without a GPU.
+// rowptr_out [nnodes+1], col_out [capacity] (may be NULL to only count), color_out [nelem_total] (may be NULL).
+extern "C" int amaru_host_prep_probe(int64_t nnodes, int nbatches, const int32_t *batch_shape, const int64_t *batch_nelem,
+                                     const int32_t *conn, int32_t *rowptr_out, int32_t *col_out, int64_t col_capacity,
+                                     int32_t *color_out, int64_t *nblk_out, int *ncolors_out) {
+    try {
+        std::vector<ShapeInfo> info(nbatches);
+        std::vector<int> nn(nbatches);
+        std::vector<const int32_t *> connp(nbatches);
+        int64_t coff = 0;
+        for (int b = 0; b < nbatches; b++) {
+            if (!amaru_shape_info(batch_shape[b], info[b])) return AMARU_ERR_UNSUPPORTED;
+            nn[b] = info[b].nn;
+            connp[b] = conn + coff;
+            coff += batch_nelem[b] * nn[b];
+        }
+        std::vector<int64_t> adj_ptr, adj;
+        amaru_build_adjacency(nnodes, nbatches, nn.data(), batch_nelem, connp.data(), adj_ptr, adj);
+        std::vector<int32_t> color;
+        const int nc = amaru_color_elements(nnodes, nbatches, nn.data(), batch_nelem, connp.data(), adj_ptr, adj, color);
+        HostPattern pat;
+        amaru_build_pattern(nnodes, nbatches, nn.data(), batch_nelem, connp.data(), adj_ptr, adj, pat);
+        if (ncolors_out) *ncolors_out = nc;
+        if (nblk_out) *nblk_out = (int64_t)pat.col.size();
+        if (rowptr_out) std::memcpy(rowptr_out, pat.rowptr.data(), pat.rowptr.size() * sizeof(int32_t));
+        if (col_out && (int64_t)pat.col.size() <= col_capacity) std::memcpy(col_out, pat.col.data(), pat.col.size() * sizeof(int32_t));
+        if (color_out) std::memcpy(color_out, color.data(), color.size() * sizeof(int32_t));
+        return AMARU_OK;
+    } catch (const AmaruError &e) {
+        return e.code;
+    }
+}

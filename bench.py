@@ -1,0 +1,279 @@
+#!/usr/bin/env python
+"""bench.py — elements/s per Newton iteration (assembly + PCG + state update) of the mechanical hot path.
+
+Workload (BASELINE.json configs[2], the configuration the metric's target is quoted on): HEX20 n^3 block on [0,1]^3
+(n=100 -> 1 M elements, 12.27 M dofs), von Mises E=210e6 nu=0.3 fy=240e3 H=0, z=0 clamped, rigid footing = prescribed
+uz on the patch x,y in [0.4,0.6] of z=1, ten equal load increments.  A "step" is ONE Newton iteration
+of the first increment: mount_K on the plastic trial state -> solve_system! (PCG to cg_rtol) -> state restore ->
+update_state!.  Every timed step does identical work (each restarts from the converged state, mech-solver.jl:333).
+
+  value  : device-timed (CUDA events on the library's stream), vectors resident in HBM
+  e2e    : the same iteration through the C ABI with HOST buffers (pinned), H2D/D2H copies inside the timed region
+  roofline: the dominant kernel (block-CSR SpMV of the PCG), algorithmic bytes / live CUDA-event duration
+  cpu_baseline: the CPU oracle (restated reference path: COO assembly -> sparse -> direct LU -> state update) on a
+           bounded sample (rank 0, N=1 only)
+
+`--impl reference` times that CPU path alone.  Multi-GPU (torchrun): weak scaling, the block grows along z with N.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "elements/sec per Newton iteration (assembly+PCG)"
+UNIT = "elements/s"
+
+
+def footing_model(n, nz=None, z0=0.0, z1=1.0):
+    from amaru_jl_b200 import Block, FEModel, MechContext, MechSolid, Mesh, NodeBC, VonMises
+    nz = nz or n
+    mesh = Mesh(Block([[0, 0, z0], [1, 1, z1]], nx=n, ny=n, nz=nz, cellshape="HEX20", tag="solids"))
+    model = FEModel(mesh, [("solids", MechSolid, VonMises, dict(E=210e6, nu=0.3, fy=240e3, H=0.0))], MechContext())
+    bcs = [(f"z=={z0}", NodeBC(ux=0, uy=0, uz=0)),
+           (f"z=={z1} and x>=0.4 and x<=0.6 and y>=0.4 and y<=0.6", NodeBC(uz=-0.01))]
+    return model, bcs
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        sm = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if r[2].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            for k, nm in enumerate(names):
+                if len(r) > 5 + k and r[5 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(self.rows)}
+
+
+def cpu_reference_step(n, steps=1, warmup=0):
+    """The restated reference CPU path on a bounded sample: mount_K (COO->sparse) + solve_system! (direct LU) +
+    update_state! of the same footing problem at n^3 HEX20 elements.  -> (elements/s, cores, seconds per step, info)"""
+    from oracle import oracle as O
+    model, bcs = footing_model(n)
+    eqid, nu, setup = model.configure_dofs(bcs)
+    Uex, Fex = model.get_bc_vals(eqid, setup)
+    om = O.OracleModel(model.flatten(), eqid, eqid.size, nu)
+    om.state_backup()
+    dUex = 0.1 * Uex
+    times = []
+    for s in range(warmup + steps):
+        t0 = time.perf_counter()
+        st, K = om.mount_K()
+        U, F = dUex.copy(), 0.1 * Fex
+        ok, msg = O.solve_system(K, U, F, nu)
+        om.state_restore()
+        dF, st2 = om.update_state(U)
+        dt = time.perf_counter() - t0
+        if s >= warmup:
+            times.append(dt)
+        assert st == 0 and ok and st2 == 0, (st, msg, st2)
+    t = float(np.mean(times))
+    return model.nelems / t, O.num_threads(), t, dict(nelems=model.nelems, ndofs=int(eqid.size))
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    n = args.cpu_size
+    val, cores, t, info = cpu_reference_step(n, steps=args.steps, warmup=min(args.warmup, 1))
+    sample = (f"HEX20 {n}^3 = {info['nelems']} elements / {info['ndofs']} dofs von Mises footing, one Newton iteration per "
+              f"step (COO mount_K + scipy SuperLU direct solve standing in for UMFPACK + update_state!), CPU oracle port")
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * t, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "configs[2]: HEX20 von Mises footing (bounded sample)", "sample_n": n},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--size", type=int, default=100, help="elements per side of the HEX20 block (100 -> 1 M elements)")
+    ap.add_argument("--cpu-size", type=int, default=12, help="elements per side of the CPU baseline sample")
+    ap.add_argument("--cg-rtol", type=float, default=1e-10)
+    ap.add_argument("--cg-maxit", type=int, default=200000)
+    ap.add_argument("--precond", default="block-jacobi", choices=["jacobi", "block-jacobi"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    from amaru_jl_b200 import lib as L
+    if not torch.cuda.is_available() or L.device_count() < 1:
+        raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        if world > 1 and not hasattr(L, "PartitionedModel"):
+            raise SystemExit("multi-GPU path not built")
+
+    pc = L.PRECOND[args.precond]
+    n = args.size
+    t_setup = time.perf_counter()
+    model, bcs = footing_model(n)
+    eqid, nu, setup = model.configure_dofs(bcs)
+    Uex, Fex = model.get_bc_vals(eqid, setup)
+    ndofs = int(eqid.size)
+    dm = L.DeviceModel(model.flatten(), eqid, ndofs, nu, device=local_rank)
+    t_setup = time.perf_counter() - t_setup
+    dUex, dFex = 0.1 * Uex, 0.1 * Fex                      # first of ten equal increments
+    dm.state_backup()
+    dm.set_device_vectors(dUex, dFex)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up: the first pass assembles the elastic K; later passes run on the plastic trial state
+    launches0 = dm.launches
+    for _ in range(max(args.warmup, 3)):
+        info = dm.newton_iteration_device(args.cg_rtol, args.cg_maxit, pc)
+    # ---- timed region (device-resident)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    dm.set_profiling(True)
+    l0 = dm.launches
+    barrier()
+    w0 = time.perf_counter()
+    dev_ms, phases = 0.0, []
+    for _ in range(args.steps):
+        info = dm.newton_iteration_device(args.cg_rtol, args.cg_maxit, pc)
+        dev_ms += info["total_ms"]
+        phases.append(info)
+    barrier()
+    wall_s = time.perf_counter() - w0
+    gpu_launches = dm.launches - l0
+    spmv_ms, spmv_n = dm.get_profile()
+    dm.set_profiling(False)
+
+    # ---- e2e: the reference-facing C-ABI calls with pinned HOST buffers, copies inside the timed region
+    hU = torch.empty(ndofs, dtype=torch.float64).pin_memory().numpy()
+    hF = torch.empty(ndofs, dtype=torch.float64).pin_memory().numpy()
+    hdF = torch.empty(ndofs, dtype=torch.float64).pin_memory().numpy()
+    barrier()
+    e0 = time.perf_counter()
+    for _ in range(args.steps):
+        hU[:] = dUex
+        hF[:] = dFex
+        dm.assemble_K()
+        dm.solve(hU, hF, args.cg_rtol, args.cg_maxit, pc)
+        dm.state_restore()
+        dm.update_state(hU, hdF)
+        resid = float(np.abs(hF[:nu] - hdF[:nu]).max())       # the Newton residual read back on the host
+    barrier()
+    e2e_s = time.perf_counter() - e0
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+
+    t_dev = dev_ms / 1e3
+    if dist is not None:
+        tt = torch.tensor([t_dev, e2e_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t_dev, e2e_s = float(tt[0]), float(tt[1])
+    nelem_total = model.nelems * world
+    value = nelem_total * args.steps / t_dev
+    e2e_val = nelem_total * args.steps / e2e_s
+
+    # ---- roofline of the dominant kernel (SpMV): algorithmic bytes per launch / average live duration
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    nd = model.ndim
+    nblk, nrows, nloc = dm.nblocks, model.nnodes, ndofs
+    spmv_bytes = nblk * (nd * nd * 8 + 4) + (nrows + 1) * 4 + nloc * (8 + 8 + 1)
+    avg_spmv_ms = spmv_ms / max(spmv_n, 1)
+    achieved = spmv_bytes / (avg_spmv_ms * 1e-3) / 1e9 if spmv_n else None
+    cg_iters = [p["cg_iters"] for p in phases]
+    # whole-iteration algorithmic bytes: assembly + update + iters * cg
+    S = 14
+    nip = model.nip_total
+    b_cg = spmv_bytes + nloc * (5 * 8 + 3 * 8 + nd * 8) + nloc * 3 * 8
+    b_asm = model.nelems * 20 * 4 + 8 * 3 * model.nnodes + nip * 8 * 7 + 8 * nblk * nd * nd
+    b_upd = model.nelems * 20 * 4 + 2 * 8 * 3 * model.nnodes + 2 * nip * 8 * S + 8 * nloc
+    b_it = b_asm + b_upd + float(np.mean(cg_iters)) * b_cg + 2 * nip * 8 * S
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"configs[2]: HEX20 {n}^3 von Mises footing, one Newton iteration per step", "elements": nelem_total,
+                   "dofs": ndofs * world, "nnz": int(dm.nnz), "cg_rtol": args.cg_rtol, "precond": args.precond,
+                   "cg_iters_per_step": cg_iters, "l2": "inputs (K = %.1f GB) larger than L2" % (dm.nnz * 8 / 1e9),
+                   "parallelism": f"dd{world}", "setup_s": round(t_setup, 2)},
+        "phases_ms": {k: float(np.mean([p[k] for p in phases])) for k in ("assemble_ms", "solve_ms", "update_ms")},
+        "iteration_gbs": b_it / (t_dev / args.steps) / 1e9,
+        "wall_s_timed_region": wall_s,
+        "gpu_launches": int(gpu_launches),
+        "clocks": sampler.summary(),
+        "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": 3 * ndofs * 8, "d2h_bytes_per_step": 3 * ndofs * 8,
+                "newton_residual": resid},
+        "roofline": {"bound": "hbm", "kernel": "k_spmv<3,true> (block-CSR SpMV + p.Ap dot)", "achieved": achieved, "peak": peak,
+                     "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "traffic": None,
+                     "bytes_per_launch": spmv_bytes, "avg_launch_ms": avg_spmv_ms, "launches_timed": int(spmv_n),
+                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)"},
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        val, cores, t, inf = cpu_reference_step(args.cpu_size, steps=1, warmup=0)
+        line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                                "sample": f"HEX20 {args.cpu_size}^3 = {inf['nelems']} elements / {inf['ndofs']} dofs, same footing "
+                                          f"problem, one Newton iteration (COO mount_K + SuperLU direct solve + update_state!) "
+                                          f"in {t:.1f} s"}
+    if rank == 0:
+        print(json.dumps(line))
+    dm.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
