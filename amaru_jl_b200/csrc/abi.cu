@@ -196,6 +196,7 @@ amaru_model *create_impl(const CreateArgs &a) {
             fx[i] = a.prescribed ? a.prescribed[i] : (uint8_t)(a.eqid[i] >= a.nu);
         }
         m->d_fixed = upload(fx.data(), fx.size());
+        m->h_fixed.swap(fx);
     }
     m->d_mat_kind = upload(a.mat_kind, (size_t)a.nmats);
     m->d_mat_par = upload(a.mat_params, (size_t)a.nmats * AMARU_MAT_NPARAMS);
@@ -207,7 +208,8 @@ amaru_model *create_impl(const CreateArgs &a) {
     m->d_diag = upload(pat.diag.data(), pat.diag.size());
     m->h_rowptr.swap(pat.rowptr);
     m->h_col.swap(pat.col);
-    const size_t kbytes = std::max<size_t>((size_t)m->nblk * m->nd * m->nd, 1) * sizeof(double);
+    // +256 B slack: the streamed SpMV reads the value array in 16-byte granules (bulk async copies)
+    const size_t kbytes = std::max<size_t>((size_t)m->nblk * m->nd * m->nd, 1) * sizeof(double) + 256;
     CUDA_CHECK(cudaMalloc(&m->d_K, kbytes));
     CUDA_CHECK(cudaMemset(m->d_K, 0, kbytes));
     m->d_A = m->d_K;
@@ -246,7 +248,8 @@ void free_model(amaru_model *m) {
                     (void *)m->d_rowptr, (void *)m->d_col, (void *)m->d_diag, (void *)m->d_K, (void *)m->d_M,
                     (void *)m->d_Minv, (void *)m->d_state, (void *)m->d_statebk, (void *)m->d_x, (void *)m->d_r,
                     (void *)m->d_z, (void *)m->d_p, (void *)m->d_q, (void *)m->d_b, (void *)m->d_f, (void *)m->d_io,
-                    (void *)m->d_U, (void *)m->d_F, (void *)m->d_partial, (void *)m->d_scal, (void *)m->d_status})
+                    (void *)m->d_U, (void *)m->d_F, (void *)m->d_U0, (void *)m->d_F0, (void *)m->d_tiles, (void *)m->d_tmeta,
+                    (void *)m->d_partial, (void *)m->d_scal, (void *)m->d_status})
         cudaFree(p);
     if (m->h_pinned) cudaFreeHost(m->h_pinned);
     if (m->stream) cudaStreamDestroy(m->stream);
@@ -316,6 +319,12 @@ int64_t amaru_nnz(const amaru_model *m) { return m ? m->nblk * m->nd * m->nd : -
 int64_t amaru_nblocks(const amaru_model *m) { return m ? m->nblk : -1; }
 int amaru_ncolors(const amaru_model *m) { return m ? m->ncolors : -1; }
 int64_t amaru_launch_count(const amaru_model *m) { return m ? m->launches : -1; }
+int64_t amaru_spmv_bytes(const amaru_model *m) {
+    if (!m) return -1;
+    const int64_t b2 = (int64_t)m->nd * m->nd, n = m->nowned * m->nd;
+    const int64_t meta = m->use_tma ? m->spmv_meta_bytes : m->nblk * 4 + (m->nowned + 1) * 4 + n;   // + fixed mask
+    return m->nblk * b2 * 8 + meta + 8 * n + 8 * n;
+}
 
 int amaru_set_state(amaru_model *m, const double *sigma, const double *eps, const double *epa, const double *dlam,
                     char *msg, int msglen) {
@@ -384,7 +393,7 @@ int amaru_assemble_M(amaru_model *m, const double *rho, char *msg, int msglen) {
         AMARU_REQUIRE(m && rho, AMARU_ERR_ARG, "null argument");
         use_device(m);
         reset_status(m);
-        if (!m->d_M) CUDA_CHECK(cudaMalloc(&m->d_M, (size_t)m->nblk * m->nd * m->nd * sizeof(double)));
+        if (!m->d_M) CUDA_CHECK(cudaMalloc(&m->d_M, (size_t)m->nblk * m->nd * m->nd * sizeof(double) + 256));
         for (Batch &B : m->batches) {
             std::vector<int64_t> perm((size_t)B.nelem);
             CUDA_CHECK(cudaMemcpy(perm.data(), B.d_perm, perm.size() * sizeof(int64_t), cudaMemcpyDeviceToHost));

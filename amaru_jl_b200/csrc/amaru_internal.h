@@ -122,6 +122,12 @@ struct amaru_model {
     int *d_status = nullptr;       // element-kernel failure flag
     int *h_pinned = nullptr;       // pinned host mirror for small reads
     int grid_rows = 0;             // persistent grid used by the row kernels
+    // streamed SpMV (spmv.cu): row tiles, per-tile records, launch geometry
+    void *d_tiles = nullptr;       // SpmvTile[ntiles]
+    int32_t *d_tmeta = nullptr;    // per-tile records: packed row entries + unique columns + 16-bit local columns
+    int ntiles = 0, tile_blks = 0, tile_rows = 0, tile_xcap = 0, grid_tma = 0, spmv_stages = 0, spmv_warps = 0, spmv_xd = 2;
+    int64_t spmv_meta_bytes = 0;   // bytes of tile records + headers streamed per SpMV
+    bool use_tma = false;
 
     // multi-GPU
     int rank = 0, nranks = 1;
@@ -136,6 +142,7 @@ struct amaru_model {
 
     // host copies kept for get_csr
     std::vector<int32_t> h_rowptr, h_col, h_eqid;
+    std::vector<uint8_t> h_fixed;
 };
 
 // ---- kernels' host entry points (one per .cu) -----------------------------------------------------------------
@@ -151,6 +158,9 @@ struct SolveInfo {
     bool converged = false;
 };
 void amaru_pcg_setup(amaru_model *m);                                // pcg.cu (allocations)
+void amaru_spmv_setup(amaru_model *m);                               // spmv.cu (tiles of the streamed SpMV)
+void amaru_spmv_launch(amaru_model *m, const double *A, const double *x, double *y, int mask, int dot, int check_done,
+                       int finalize);                                 // spmv.cu
 void amaru_pcg_solve(amaru_model *m, double rtol, int maxit, int precond, SolveInfo &info);  // pcg.cu
 void amaru_spmv(amaru_model *m, const double *A, const double *x, double *y, int mask_mode);  // pcg.cu
 void amaru_eq_to_nodes(amaru_model *m, const double *d_eq, double *d_nodes);                  // pcg.cu

@@ -1,15 +1,13 @@
-// K4-K8: the linear-system step.  Replaces solve_system! (reference src/solver.jl:5-79): the sparse direct
+// K5-K8: the linear-system step.  Replaces solve_system! (reference src/solver.jl:5-79): the sparse direct
 // lu(K11)\(F1 - K12*U2) (solver.jl:38-43) becomes a Jacobi / block-Jacobi preconditioned CG on the device, and the
 // K12/K21/K22 slice products (solver.jl:32,38,57) become full-matrix products with the prescribed dofs masked.
 //
-// Storage: node-blocked CSR (nd x nd blocks, int32 block columns) in node-major dof order; the reference's
-// unknown-first eq_id numbering exists only at the ABI (k_eq_to_nodes / k_nodes_to_eq).  Prescribed dofs stay in
-// the matrix; CG runs on the full vector space with rows of prescribed dofs masked to zero, which is algebraically the
-// K11 system.
+// Storage: node-blocked CSR (nd x nd blocks) in node-major dof order; the reference's unknown-first eq_id numbering
+// exists only at the ABI (k_eq_to_nodes / k_nodes_to_eq).  Prescribed dofs stay in the matrix; CG runs on the full
+// vector space with the rows of prescribed dofs masked to zero, which is algebraically the K11 system.
 //
-// Kernels (all FP64, hand-written):
-//   k_spmv         one warp per block row, persistent grid; lanes own one (block-in-group, r, c) slot so every lane
-//                  streams a contiguous run of the value array; fused p·(Ap) partial dot                          (K4, K5)
+// Kernels here (all FP64, hand-written; the SpMV lives in spmv.cu):
+//   k_cg_init      r = b - A[0;U2] on free dofs, z = M⁻¹r, p = z, partial r·z and b·b
 //   k_cg_update    x += αp, r -= αq, z = M⁻¹r, partial r·z and r·r                                               (K5-K7)
 //   k_cg_pupdate   p = z + βp                                                                                    (K6)
 //   k_block_inverse  Jacobi / block-Jacobi setup from the diagonal blocks, prescribed rows/cols -> identity      (K7)
@@ -18,156 +16,16 @@
 // polls the convergence flag every CG_BATCH iterations; kernels of iterations launched past convergence exit at once.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
-#include "amaru_internal.h"
-
-struct CgScalars {
-    double rz_old, pq, rz_new, rr, bb, alpha, beta, tol2;
-    double acc[4];               // scratch for all-reduce (multi-GPU)
-    unsigned long long maxabs_bits;
-    int done;                    // 0 running, 1 converged, 2 maxit, 3 breakdown
-    int iters, maxit;
-    unsigned int counter[4];
-    int nanflag;
-};
+#include "reduce.cuh"
 
 namespace {
 
 constexpr int CG_BATCH = 20;
 constexpr int ROW_THREADS = 256;
 
-__device__ __forceinline__ double warp_sum(double v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
-
-// block-wide sum of NV values per thread; result valid in thread 0
-template <int NV, int NT>
-__device__ __forceinline__ void block_sum(double (&v)[NV]) {
-    __shared__ double sh[NV][NT / 32];
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-#pragma unroll
-    for (int k = 0; k < NV; k++) {
-        const double s = warp_sum(v[k]);
-        if (lane == 0) sh[k][w] = s;
-    }
-    __syncthreads();
-    if (w == 0) {
-#pragma unroll
-        for (int k = 0; k < NV; k++) {
-            double s = lane < NT / 32 ? sh[k][lane] : 0.0;
-            s = warp_sum(s);
-            v[k] = s;
-        }
-    }
-    __syncthreads();
-}
-
-// publishes this block's partial sums and returns true (for all threads) in the last block to arrive
-template <int NV>
-__device__ __forceinline__ bool publish_partials(const double (&v)[NV], double *partial, unsigned int *counter) {
-    __shared__ bool last;
-    if (threadIdx.x == 0) {
-#pragma unroll
-        for (int k = 0; k < NV; k++) partial[(size_t)k * gridDim.x + blockIdx.x] = v[k];
-        __threadfence();
-        const unsigned int t = atomicInc(counter, gridDim.x - 1);
-        last = (t == gridDim.x - 1);
-    }
-    __syncthreads();
-    return last;
-}
-
-// fixed-order sum of the per-block partials (called by every thread of the last block); result valid in thread 0
-template <int NV, int NT>
-__device__ __forceinline__ void sum_partials(double (&v)[NV], const double *partial) {
-#pragma unroll
-    for (int k = 0; k < NV; k++) {
-        double s = 0.0;
-        for (int i = threadIdx.x; i < (int)gridDim.x; i += NT) s += __ldcg(&partial[(size_t)k * gridDim.x + i]);
-        v[k] = s;
-    }
-    block_sum<NV, NT>(v);
-}
-
-// ------------------------------------------------------------------------------------------------ SpMV
-template <int BS, bool DOT>
-__global__ void __launch_bounds__(ROW_THREADS)
-k_spmv(int64_t nrows, const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col,
-       const double *__restrict__ A, const double *__restrict__ x, double *__restrict__ y,
-       const uint8_t *__restrict__ fixed, int mask_rows, double *partial, CgScalars *scal, int check_done,
-       int finalize) {
-    if (check_done && scal->done) return;
-    constexpr int B2 = BS * BS;
-    constexpr int BPI = 32 / B2;   // blocks per warp step: 3 (3x3) or 8 (2x2)
-    constexpr int ACT = BPI * B2;  // active lanes: 27 or 32
-    const int lane = threadIdx.x & 31;
-    const int64_t gw = (int64_t)blockIdx.x * (ROW_THREADS / 32) + (threadIdx.x >> 5);
-    const int64_t nw = (int64_t)gridDim.x * (ROW_THREADS / 32);
-    const int bl = lane / B2, rc = lane - bl * B2;
-    const int c = rc % BS;
-    const bool act = lane < ACT;
-    double dsum[1] = {0.0};
-    for (int64_t row = gw; row < nrows; row += nw) {
-        const int32_t s = rowptr[row], e = rowptr[row + 1];
-        double acc = 0.0;
-        if (act) {
-            int32_t k = s + bl;
-            for (; k + 3 * BPI < e; k += 4 * BPI) {
-                const int32_t c0 = __ldg(col + k), c1 = __ldg(col + k + BPI), c2 = __ldg(col + k + 2 * BPI),
-                              c3 = __ldg(col + k + 3 * BPI);
-                const double v0 = __ldg(A + (int64_t)k * B2 + rc), v1 = __ldg(A + (int64_t)(k + BPI) * B2 + rc),
-                             v2 = __ldg(A + (int64_t)(k + 2 * BPI) * B2 + rc),
-                             v3 = __ldg(A + (int64_t)(k + 3 * BPI) * B2 + rc);
-                const double x0 = x[(int64_t)c0 * BS + c], x1 = x[(int64_t)c1 * BS + c], x2 = x[(int64_t)c2 * BS + c],
-                             x3 = x[(int64_t)c3 * BS + c];
-                acc += v0 * x0;
-                acc += v1 * x1;
-                acc += v2 * x2;
-                acc += v3 * x3;
-            }
-            for (; k < e; k += BPI) acc += __ldg(A + (int64_t)k * B2 + rc) * x[(int64_t)__ldg(col + k) * BS + c];
-        }
-        double tot;
-        if constexpr (BS == 3) {
-            const double t1 = __shfl_down_sync(0xffffffffu, acc, 9), t2 = __shfl_down_sync(0xffffffffu, acc, 18);
-            const double sm = acc + t1 + t2;                       // valid in lanes 0..8 (slot rc)
-            const double u1 = __shfl_down_sync(0xffffffffu, sm, 1), u2 = __shfl_down_sync(0xffffffffu, sm, 2);
-            tot = sm + u1 + u2;                                    // valid in lanes 0,3,6 (row r = lane/3)
-        } else {
-            double sm = acc;
-            sm += __shfl_xor_sync(0xffffffffu, sm, 4);
-            sm += __shfl_xor_sync(0xffffffffu, sm, 8);
-            sm += __shfl_xor_sync(0xffffffffu, sm, 16);
-            tot = sm + __shfl_xor_sync(0xffffffffu, sm, 1);         // valid in lanes 0 and 2
-        }
-        const bool writer = (BS == 3) ? (lane < 9 && lane % 3 == 0) : (lane == 0 || lane == 2);
-        if (writer) {
-            const int r = (BS == 3) ? lane / 3 : lane / 2;
-            const int64_t i = row * BS + r;
-            if (mask_rows && fixed[i]) tot = 0.0;
-            y[i] = tot;
-            if (DOT) dsum[0] += tot * x[i];
-        }
-    }
-    if (DOT) {
-        block_sum<1, ROW_THREADS>(dsum);
-        if (publish_partials<1>(dsum, partial, &scal->counter[0])) {
-            sum_partials<1, ROW_THREADS>(dsum, partial);
-            if (threadIdx.x == 0) {
-                scal->pq = dsum[0];
-                if (finalize) {
-                    if (!(dsum[0] > 0.0)) scal->done = 3;          // not SPD / breakdown
-                    scal->alpha = scal->rz_old / dsum[0];
-                }
-            }
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------------------ vector kernels
 // z = M⁻¹ r for one node
 template <int BS, bool BLOCKJ>
 __device__ __forceinline__ void apply_minv(const double *__restrict__ Minv, int64_t node, const double *r, double *z) {
@@ -360,6 +218,10 @@ __global__ void k_axpby_matrix(int64_t n, double a, const double *__restrict__ K
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
         A[i] = a * K[i] + b * M[i];
 }
+__global__ void k_zero_free(int64_t n, const uint8_t *__restrict__ fixed, double *x) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        if (!fixed[i]) x[i] = 0.0;
+}
 __global__ void k_maxabs_nan(int64_t n, const double *__restrict__ v, const uint8_t *__restrict__ fixed, int only_free,
                              CgScalars *scal) {
     double mx = 0.0;
@@ -388,6 +250,9 @@ __global__ void k_reset_flags(CgScalars *scal) {
 int blocks_for(amaru_model *m, int64_t n, int threads) {
     return (int)std::max<int64_t>(1, std::min<int64_t>((n + threads - 1) / threads, (int64_t)m->nsm * 8));
 }
+int node_grid(amaru_model *m, int64_t n) {
+    return (int)std::max<int64_t>(1, std::min<int64_t>((n + ROW_THREADS - 1) / ROW_THREADS, (int64_t)m->nsm * 8));
+}
 
 }  // namespace
 
@@ -403,56 +268,27 @@ void amaru_pcg_setup(amaru_model *m) {
     CUDA_CHECK(cudaMalloc(&m->d_f, nv));
     for (double *v : {m->d_x, m->d_r, m->d_z, m->d_p, m->d_q, m->d_b, m->d_f}) CUDA_CHECK(cudaMemset(v, 0, nv));
     CUDA_CHECK(cudaMalloc(&m->d_Minv, (size_t)std::max<int64_t>(m->nowned, 1) * m->nd * m->nd * sizeof(double)));
-    // persistent grid of the row kernels: one full wave
-    int occ = 0;
-    if (m->nd == 3)
-        CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_spmv<3, true>, ROW_THREADS, 0));
-    else
-        CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_spmv<2, true>, ROW_THREADS, 0));
-    if (occ < 1) occ = 1;
-    m->grid_rows = m->nsm * occ;
-    CUDA_CHECK(cudaMalloc(&m->d_partial, (size_t)4 * m->grid_rows * sizeof(double)));
+    amaru_spmv_setup(m);
+    const int maxgrid = std::max(std::max(m->grid_rows, m->grid_tma), m->nsm * 8);
+    CUDA_CHECK(cudaMalloc(&m->d_partial, (size_t)4 * maxgrid * sizeof(double)));
     CUDA_CHECK(cudaMalloc(&m->d_scal, sizeof(CgScalars)));
     CUDA_CHECK(cudaMemset(m->d_scal, 0, sizeof(CgScalars)));
     CUDA_CHECK(cudaMallocHost(&m->h_pinned, sizeof(CgScalars) + 64));
 }
 
-static int row_grid(amaru_model *m, int64_t nrows) {
-    const int64_t need = (nrows + (ROW_THREADS / 32) - 1) / (ROW_THREADS / 32);
-    return (int)std::max<int64_t>(1, std::min<int64_t>(need, m->grid_rows));
-}
-static int node_grid(amaru_model *m, int64_t n) {
-    return (int)std::max<int64_t>(1, std::min<int64_t>((n + ROW_THREADS - 1) / ROW_THREADS, m->grid_rows));
-}
-
 // y = A x on the owned rows; mask_mode 1 zeroes the rows of prescribed dofs.  x must hold valid ghost entries.
 void amaru_spmv(amaru_model *m, const double *A, const double *x, double *y, int mask_mode) {
-    const int g = row_grid(m, m->nowned);
-    if (m->nd == 3)
-        k_spmv<3, false><<<g, ROW_THREADS, 0, m->stream>>>(m->nowned, m->d_rowptr, m->d_col, A, x, y, m->d_fixed,
-                                                            mask_mode, m->d_partial, m->d_scal, 0, 0);
-    else
-        k_spmv<2, false><<<g, ROW_THREADS, 0, m->stream>>>(m->nowned, m->d_rowptr, m->d_col, A, x, y, m->d_fixed,
-                                                            mask_mode, m->d_partial, m->d_scal, 0, 0);
-    m->launches++;
-    CUDA_CHECK(cudaGetLastError());
+    amaru_spmv_launch(m, A, x, y, mask_mode, 0, 0, 0);
 }
 
 static void spmv_dot(amaru_model *m, const double *A, const double *x, double *y, int finalize) {
-    const int g = row_grid(m, m->nowned);
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (m->profiling) {
         CUDA_CHECK(cudaEventCreate(&e0));
         CUDA_CHECK(cudaEventCreate(&e1));
         CUDA_CHECK(cudaEventRecord(e0, m->stream));
     }
-    if (m->nd == 3)
-        k_spmv<3, true><<<g, ROW_THREADS, 0, m->stream>>>(m->nowned, m->d_rowptr, m->d_col, A, x, y, m->d_fixed, 1,
-                                                           m->d_partial, m->d_scal, 1, finalize);
-    else
-        k_spmv<2, true><<<g, ROW_THREADS, 0, m->stream>>>(m->nowned, m->d_rowptr, m->d_col, A, x, y, m->d_fixed, 1,
-                                                           m->d_partial, m->d_scal, 1, finalize);
-    m->launches++;
+    amaru_spmv_launch(m, A, x, y, 1, 1, 1, finalize);
     if (m->profiling) {
         CUDA_CHECK(cudaEventRecord(e1, m->stream));
         m->ev_pool.push_back(e0);
@@ -482,8 +318,7 @@ static void cg_loop(amaru_model *m, double rtol, int maxit, SolveInfo &info) {
     const bool multi = m->nranks > 1;
     const int fin = multi ? 0 : 1;
     CgScalars *h = reinterpret_cast<CgScalars *>(m->h_pinned);
-    // t = A*[0;U2] (d_x holds U2 at prescribed dofs, anything at free dofs -> zero them first through init? no:
-    // the caller zeroed the free entries), r = b - t on free dofs
+    // t = A*[0;U2] (the caller zeroed the free entries of d_x), r = b - t on the free dofs
     if (multi) amaru_halo_exchange(m, m->d_x);
     amaru_spmv(m, m->d_A, m->d_x, m->d_q, 0);
     k_cg_init<BS, BJ><<<gn, ROW_THREADS, 0, m->stream>>>(m->nowned, m->d_b, m->d_q, m->d_fixed, m->d_Minv, m->d_x, m->d_r,
@@ -542,14 +377,19 @@ static void cg_loop(amaru_model *m, double rtol, int maxit, SolveInfo &info) {
     }
 }
 
+void amaru_zero_free(amaru_model *m, double *x) {
+    const int64_t n = m->nnodes * m->nd;
+    k_zero_free<<<blocks_for(m, n, 256), 256, 0, m->stream>>>(n, m->d_fixed, x);
+    m->launches++;
+}
+
 // Solve on node-major vectors: in  d_x = prescribed values at prescribed dofs (free entries ignored),
 //                                  d_b = known forces at free dofs;
 //                              out d_x = full displacement vector, d_q = A*x (reactions at prescribed dofs).
 void amaru_pcg_solve(amaru_model *m, double rtol, int maxit, int precond, SolveInfo &info) {
     build_preconditioner(m, precond);
     const int64_t nloc = m->nowned * m->nd;
-    // zero the free entries of x so that the first product is K*[0;U2]
-    amaru_zero_free(m, m->d_x);
+    amaru_zero_free(m, m->d_x);   // the first product must be K*[0;U2]
     const bool bj = precond == AMARU_PRECOND_BLOCK_JACOBI;
     if (m->nd == 3) {
         if (bj) cg_loop<3, true>(m, rtol, maxit, info);
@@ -573,18 +413,6 @@ void amaru_pcg_solve(amaru_model *m, double rtol, int maxit, int precond, SolveI
     info.maxabs = h->nanflag ? NAN : mx;
 }
 
-namespace {
-__global__ void k_zero_free(int64_t n, const uint8_t *__restrict__ fixed, double *x) {
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-        if (!fixed[i]) x[i] = 0.0;
-}
-}  // namespace
-void amaru_zero_free(amaru_model *m, double *x) {
-    const int64_t n = m->nnodes * m->nd;
-    k_zero_free<<<blocks_for(m, n, 256), 256, 0, m->stream>>>(n, m->d_fixed, x);
-    m->launches++;
-}
-
 void amaru_eq_to_nodes(amaru_model *m, const double *d_eq, double *d_nodes) {
     const int64_t n = m->nnodes * m->nd;
     k_eq_to_nodes<<<blocks_for(m, n, 256), 256, 0, m->stream>>>(n, m->d_eqid, d_eq, d_nodes);
@@ -605,8 +433,7 @@ void amaru_combine_matrix(amaru_model *m) {
         m->d_A = m->d_K;
     } else {
         AMARU_REQUIRE(m->d_M != nullptr, AMARU_ERR_ARG, "set_system_matrix: mass matrix not assembled");
-        static_assert(sizeof(double) == 8, "");
-        if (m->d_A == m->d_K || m->d_A == nullptr) CUDA_CHECK(cudaMalloc(&m->d_A, (size_t)n * sizeof(double)));
+        if (m->d_A == m->d_K || m->d_A == nullptr) CUDA_CHECK(cudaMalloc(&m->d_A, (size_t)n * sizeof(double) + 256));
         k_axpby_matrix<<<blocks_for(m, n, 256), 256, 0, m->stream>>>(n, m->sysA, m->d_K, m->sysB, m->d_M, m->d_A);
         m->launches++;
         CUDA_CHECK(cudaGetLastError());

@@ -64,6 +64,7 @@ SYMBOLS = {
     "amaru_time_kernel": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _dp, C.c_char_p, C.c_int]),
     "amaru_set_profiling": (C.c_int, [_vp, C.c_int]),
     "amaru_get_profile": (C.c_int, [_vp, _dp, _i64p]),
+    "amaru_spmv_bytes": (C.c_int64, [_vp]),
     "amaru_launch_count": (C.c_int64, [_vp]),
 }
 
@@ -156,6 +157,10 @@ class DeviceModel:
     @property
     def ncolors(self):
         return self.lib.amaru_ncolors(self.h)
+
+    @property
+    def spmv_bytes(self):
+        return self.lib.amaru_spmv_bytes(self.h)
 
     @property
     def launches(self):

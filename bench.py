@@ -231,7 +231,7 @@ def main():
     peak = float(peaks.get("hbm_gbs", 6650.0))
     nd = model.ndim
     nblk, nrows, nloc = dm.nblocks, model.nnodes, ndofs
-    spmv_bytes = nblk * (nd * nd * 8 + 4) + (nrows + 1) * 4 + nloc * (8 + 8 + 1)
+    spmv_bytes = int(dm.spmv_bytes)   # values + tile records of the stored format + x once + y once
     avg_spmv_ms = spmv_ms / max(spmv_n, 1)
     achieved = spmv_bytes / (avg_spmv_ms * 1e-3) / 1e9 if spmv_n else None
     cg_iters = [p["cg_iters"] for p in phases]

@@ -177,6 +177,9 @@ int amaru_time_kernel(amaru_model *m, int kind, int precond, int reps, double *a
  * returns the summed duration (ms) and the number of SpMV launches since profiling was switched on. */
 int amaru_set_profiling(amaru_model *m, int on);
 int amaru_get_profile(amaru_model *m, double *spmv_ms_total, int64_t *spmv_launches);
+/* Algorithmic bytes one SpMV launch must move: matrix values + column/row metadata of the storage
+ * format actually used + x read once + y written once. */
+int64_t amaru_spmv_bytes(const amaru_model *m);
 /* number of kernels launched by this handle since creation (the bench's gpu_launches claim) */
 int64_t amaru_launch_count(const amaru_model *m);
 
