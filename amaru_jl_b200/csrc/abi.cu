@@ -239,6 +239,7 @@ amaru_model *create_impl(const CreateArgs &a) {
 void free_model(amaru_model *m) {
     cudaSetDevice(m->device);
     if (m->stream) cudaStreamSynchronize(m->stream);
+    amaru_comm_destroy(m);
     for (Batch &B : m->batches) {
         cudaFree(B.d_conn); cudaFree(B.d_emat); cudaFree(B.d_map); cudaFree(B.d_perm); cudaFree(B.d_owned);
         cudaFree(B.d_rho); cudaFree(B.d_dNdR); cudaFree(B.d_N); cudaFree(B.d_w);
@@ -261,8 +262,23 @@ int solve_device(amaru_model *m, double cg_rtol, int cg_maxit, int precond, Solv
     amaru_eq_to_nodes(m, m->d_U, m->d_x);
     amaru_eq_to_nodes(m, m->d_F, m->d_b);
     amaru_pcg_solve(m, cg_rtol, cg_maxit, precond, info);
-    amaru_nodes_to_eq(m, m->d_x, m->d_U, 1);   // U[1:nu]     .= U1   (solver.jl:74)
-    amaru_nodes_to_eq(m, m->d_q, m->d_F, 2);   // F[nu+1:end] .= F2   (solver.jl:75)
+    if (m->nranks == 1) {
+        amaru_nodes_to_eq(m, m->d_x, m->d_U, 1);   // U[1:nu]     .= U1   (solver.jl:74)
+        amaru_nodes_to_eq(m, m->d_q, m->d_F, 2);   // F[nu+1:end] .= F2   (solver.jl:75)
+    } else {
+        // every rank contributes the entries of the rows it owns; one all-reduce per vector rebuilds the global ones
+        const size_t bytes = (size_t)m->ndofs * sizeof(double);
+        CUDA_CHECK(cudaMemsetAsync(m->d_io, 0, bytes, m->stream));
+        amaru_nodes_to_eq(m, m->d_x, m->d_io, 1);
+        amaru_allreduce_sum(m, m->d_io, m->ndofs);
+        if (m->nu > 0) CUDA_CHECK(cudaMemcpyAsync(m->d_U, m->d_io, (size_t)m->nu * sizeof(double), cudaMemcpyDeviceToDevice, m->stream));
+        CUDA_CHECK(cudaMemsetAsync(m->d_io, 0, bytes, m->stream));
+        amaru_nodes_to_eq(m, m->d_q, m->d_io, 2);
+        amaru_allreduce_sum(m, m->d_io, m->ndofs);
+        if (m->ndofs > m->nu)
+            CUDA_CHECK(cudaMemcpyAsync(m->d_F + m->nu, m->d_io + m->nu, (size_t)(m->ndofs - m->nu) * sizeof(double),
+                                       cudaMemcpyDeviceToDevice, m->stream));
+    }
     if (!info.converged) return AMARU_FAIL_CG_NOCONV;
     if (!(info.maxabs <= 1e8)) return AMARU_FAIL_SINGULAR;   // solver.jl:68-71 (NaN also lands here)
     return AMARU_OK;
@@ -274,9 +290,14 @@ int update_device(amaru_model *m) {
     amaru_launch_update(m, m->d_x, m->d_f, 0);
     CUDA_CHECK(cudaMemsetAsync(m->d_F, 0, (size_t)m->ndofs * sizeof(double), m->stream));
     amaru_nodes_to_eq(m, m->d_f, m->d_F, 0);
+    if (m->nranks > 1) {
+        amaru_allreduce_sum(m, m->d_F, m->ndofs);
+        amaru_allreduce_max_int(m, m->d_status);
+    }
     const int st = read_status(m);
     if (st) return st;
-    if (amaru_check_nan(m, m->d_f, m->nowned * m->nd)) return AMARU_FAIL_NAN;
+    const int nan = m->nranks > 1 ? amaru_check_nan(m, m->d_F, m->ndofs) : amaru_check_nan(m, m->d_f, m->nowned * m->nd);
+    if (nan) return AMARU_FAIL_NAN;
     return AMARU_OK;
 }
 
@@ -304,6 +325,35 @@ int amaru_create(int ndim, int stressmodel, double thickness, int64_t nnodes, co
         CreateArgs a{ndim, stressmodel, thickness, nnodes, nnodes, coords, nbatches, batch_shape, batch_nelem, conn,
                      elem_mat, nmats, mat_kind, mat_params, eqid, nullptr, ndofs, nu, device, 0, 1};
         *out = create_impl(a);
+        return AMARU_OK;
+    });
+}
+
+int amaru_create_partitioned(int ndim, int stressmodel, double thickness, int64_t nnodes, int64_t nowned,
+                             const double *coords, int nbatches, const int32_t *batch_shape, const int64_t *batch_nelem,
+                             const int32_t *conn, const int32_t *elem_mat, int nmats, const int32_t *mat_kind,
+                             const double *mat_params, const int32_t *eqid, int64_t ndofs, int64_t nu, int rank, int nranks,
+                             int nneigh, const int32_t *neigh_rank, const int64_t *send_ptr, const int32_t *send_nodes,
+                             const int64_t *recv_start, const int64_t *recv_count, const void *nccl_uid, int device,
+                             amaru_model **out, char *msg, int msglen) {
+    return guarded(msg, msglen, [&]() {
+        AMARU_REQUIRE(out != nullptr, AMARU_ERR_ARG, "amaru_create_partitioned: out is NULL");
+        *out = nullptr;
+        AMARU_REQUIRE(nranks >= 1 && rank >= 0 && rank < nranks, AMARU_ERR_ARG, "amaru_create_partitioned: bad rank");
+        AMARU_REQUIRE(nowned >= 0 && nowned <= nnodes, AMARU_ERR_ARG, "amaru_create_partitioned: nowned out of range");
+        AMARU_REQUIRE(nu >= 0 && nu <= ndofs, AMARU_ERR_ARG, "amaru_create_partitioned: nu out of range");
+        AMARU_REQUIRE(nneigh == 0 || (neigh_rank && send_ptr && recv_start && recv_count && nccl_uid), AMARU_ERR_ARG,
+                      "amaru_create_partitioned: null halo lists");
+        CreateArgs a{ndim, stressmodel, thickness, nnodes, nowned, coords, nbatches, batch_shape, batch_nelem, conn,
+                     elem_mat, nmats, mat_kind, mat_params, eqid, nullptr, ndofs, nu, device, rank, nranks};
+        amaru_model *m = create_impl(a);
+        try {
+            if (nranks > 1) amaru_comm_setup(m, nneigh, neigh_rank, send_ptr, send_nodes, recv_start, recv_count, nccl_uid);
+        } catch (...) {
+            free_model(m);
+            throw;
+        }
+        *out = m;
         return AMARU_OK;
     });
 }
@@ -382,6 +432,7 @@ int amaru_assemble_K(amaru_model *m, char *msg, int msglen) {
         reset_status(m);
         amaru_launch_assemble(m, 0);
         amaru_combine_matrix(m);
+        if (m->nranks > 1) amaru_allreduce_max_int(m, m->d_status);
         const int st = read_status(m);
         if (st) throw AmaruError{st, status_text(st)};
         return AMARU_OK;
@@ -562,6 +613,8 @@ int amaru_newton_iteration_device(amaru_model *m, double cg_rtol, int cg_maxit, 
         reset_status(m);
         amaru_launch_assemble(m, 0);                                   // mount_K            (mech-solver.jl:327)
         amaru_combine_matrix(m);
+        if (m->nranks > 1) amaru_allreduce_max_int(m, m->d_status);
+        const int as = read_status(m);                                 // assembly status (update_device resets the flag)
         CUDA_CHECK(cudaEventRecord(ev[1], m->stream));
         CUDA_CHECK(cudaMemcpyAsync(m->d_U, m->d_U0, bytes, cudaMemcpyDeviceToDevice, m->stream));
         CUDA_CHECK(cudaMemcpyAsync(m->d_F, m->d_F0, bytes, cudaMemcpyDeviceToDevice, m->stream));
@@ -584,7 +637,6 @@ int amaru_newton_iteration_device(amaru_model *m, double cg_rtol, int cg_maxit, 
         for (auto &e : ev) cudaEventDestroy(e);
         if (iters) *iters = info.iters;
         if (relres) *relres = info.relres;
-        const int as = read_status(m);
         if (as) st = as;
         if (st == AMARU_OK) st = st2;
         if (st) throw AmaruError{st, status_text(st)};

@@ -172,5 +172,9 @@ void amaru_time_cg_kernel(amaru_model *m, int kind, int precond, int reps);  // 
 
 // halo exchange (halo.cu) — no-ops for nranks == 1
 void amaru_halo_exchange(amaru_model *m, double *d_v);
-void amaru_allreduce_sum(amaru_model *m, double *d_vals, int n);
+void amaru_allreduce_sum(amaru_model *m, double *d_vals, int64_t n);
+void amaru_allreduce_max(amaru_model *m, double *d_vals, int64_t n);
 void amaru_allreduce_max_int(amaru_model *m, int *d_val);
+void amaru_comm_setup(amaru_model *m, int nneigh, const int32_t *neigh_rank, const int64_t *send_ptr,
+                      const int32_t *send_nodes, const int64_t *recv_start, const int64_t *recv_count, const void *uid);
+void amaru_comm_destroy(amaru_model *m);

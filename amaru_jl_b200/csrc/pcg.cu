@@ -242,6 +242,9 @@ __global__ void k_maxabs_nan(int64_t n, const double *__restrict__ v, const uint
         if (nan) atomicOr(&scal->nanflag, 1);
     }
 }
+__global__ void k_stage_maxabs(CgScalars *scal) {
+    scal->acc[0] = scal->nanflag ? __longlong_as_double(0x7ff0000000000000LL) : __longlong_as_double((long long)scal->maxabs_bits);
+}
 __global__ void k_reset_flags(CgScalars *scal) {
     scal->maxabs_bits = 0ull;
     scal->nanflag = 0;
@@ -405,11 +408,17 @@ void amaru_pcg_solve(amaru_model *m, double rtol, int maxit, int precond, SolveI
     k_reset_flags<<<1, 1, 0, m->stream>>>(m->d_scal);
     k_maxabs_nan<<<blocks_for(m, nloc, 256), 256, 0, m->stream>>>(nloc, m->d_x, m->d_fixed, 1, m->d_scal);
     m->launches += 2;
+    if (m->nranks > 1) {   // max over ranks (a NaN anywhere becomes +inf everywhere)
+        k_stage_maxabs<<<1, 1, 0, m->stream>>>(m->d_scal);
+        amaru_allreduce_max(m, m->d_scal->acc, 1);
+        m->launches++;
+    }
     CgScalars *h = reinterpret_cast<CgScalars *>(m->h_pinned);
     CUDA_CHECK(cudaMemcpyAsync(h, m->d_scal, sizeof(CgScalars), cudaMemcpyDeviceToHost, m->stream));
     CUDA_CHECK(cudaStreamSynchronize(m->stream));
     double mx;
     std::memcpy(&mx, &h->maxabs_bits, sizeof(double));
+    if (m->nranks > 1) mx = h->acc[0];
     info.maxabs = h->nanflag ? NAN : mx;
 }
 

@@ -35,10 +35,10 @@ SYMBOLS = {
     "amaru_create": (C.c_int, [C.c_int, C.c_int, C.c_double, C.c_int64, _dp, C.c_int, _i32p, _i64p, _i32p, _i32p,
                                C.c_int, _i32p, _dp, _i32p, C.c_int64, C.c_int64, C.c_int, C.POINTER(_vp), C.c_char_p,
                                C.c_int]),
-    "amaru_create_partitioned": (C.c_int, [C.c_int, C.c_int, C.c_double, C.c_int64, C.c_int64, _dp, _i64p, _i32p,
-                                           C.c_int, _i32p, _i64p, _i32p, _i32p, _u8p, C.c_int, _i32p, _dp, _i32p, _u8p,
-                                           C.c_int64, C.c_int64, C.c_int, C.c_int, _vp, C.c_int, C.POINTER(_vp),
-                                           C.c_char_p, C.c_int]),
+    "amaru_create_partitioned": (C.c_int, [C.c_int, C.c_int, C.c_double, C.c_int64, C.c_int64, _dp,
+                                           C.c_int, _i32p, _i64p, _i32p, _i32p, C.c_int, _i32p, _dp, _i32p,
+                                           C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, _i32p, _i64p, _i32p, _i64p,
+                                           _i64p, _vp, C.c_int, C.POINTER(_vp), C.c_char_p, C.c_int]),
     "amaru_nccl_unique_id": (C.c_int, [_vp, C.c_char_p, C.c_int]),
     "amaru_destroy": (C.c_int, [_vp]),
     "amaru_nip_total": (C.c_int64, [_vp]),
@@ -95,6 +95,15 @@ def _d(a):
     return a.ctypes.data_as(_dp) if a is not None else None
 
 
+def nccl_unique_id() -> bytes:
+    """128-byte ncclUniqueId (rank 0 makes it, the host broadcasts it to the other ranks)."""
+    buf, msg = C.create_string_buffer(128), C.create_string_buffer(256)
+    st = load().amaru_nccl_unique_id(C.cast(buf, _vp), msg, 256)
+    if st != OK:
+        raise AmaruError(f"amaru_nccl_unique_id [{st}] {msg.value.decode(errors='replace')}")
+    return bytes(buf.raw)
+
+
 class AmaruStatus(AmaruError):
     """A non-zero status from the library: ``code > 0`` = ReturnStatus failure, ``code < 0`` = usage / CUDA error."""
 
@@ -106,7 +115,10 @@ class AmaruStatus(AmaruError):
 class DeviceModel:
     """One stage's device handle (``amaru_create`` ... ``amaru_destroy``)."""
 
-    def __init__(self, flat: dict, eqid: np.ndarray, ndofs: int, nu: int, device: int = 0):
+    def __init__(self, flat: dict, eqid: np.ndarray, ndofs: int, nu: int, device: int = 0, view=None, nccl_uid=None):
+        """Single-GPU handle (``amaru_create``), or — with ``view`` (partition.LocalView) and the 128-byte ``nccl_uid`` —
+        this rank's handle of a partitioned model (``amaru_create_partitioned``); ``flat``/``eqid`` are then the LOCAL
+        arrays from ``partition.local_flat`` while ``ndofs``/``nu`` stay global."""
         self.lib = load()
         self._msg = C.create_string_buffer(512)
         self.ndofs, self.nu = int(ndofs), int(nu)
@@ -119,12 +131,29 @@ class DeviceModel:
         mpar = np.ascontiguousarray(flat["mat_params"], dtype=np.float64).reshape(-1)
         eq = np.ascontiguousarray(eqid, dtype=np.int32).reshape(-1)
         h = _vp()
-        st = self.lib.amaru_create(int(flat["ndim"]), int(flat["stressmodel"]), float(flat["thickness"]),
-                                   coords.shape[0], _d(coords), len(bshape), bshape.ctypes.data_as(_i32p),
-                                   bnelem.ctypes.data_as(_i64p), conn.ctypes.data_as(_i32p),
-                                   emat.ctypes.data_as(_i32p), len(mkind), mkind.ctypes.data_as(_i32p), _d(mpar),
-                                   eq.ctypes.data_as(_i32p), self.ndofs, self.nu, int(device), C.byref(h), self._msg,
-                                   len(self._msg))
+        self.view = view
+        if view is None:
+            st = self.lib.amaru_create(int(flat["ndim"]), int(flat["stressmodel"]), float(flat["thickness"]),
+                                       coords.shape[0], _d(coords), len(bshape), bshape.ctypes.data_as(_i32p),
+                                       bnelem.ctypes.data_as(_i64p), conn.ctypes.data_as(_i32p),
+                                       emat.ctypes.data_as(_i32p), len(mkind), mkind.ctypes.data_as(_i32p), _d(mpar),
+                                       eq.ctypes.data_as(_i32p), self.ndofs, self.nu, int(device), C.byref(h), self._msg,
+                                       len(self._msg))
+        else:
+            neigh = np.ascontiguousarray(view.neigh, dtype=np.int32)
+            sptr = np.ascontiguousarray(view.send_ptr, dtype=np.int64)
+            snod = np.ascontiguousarray(view.send_nodes, dtype=np.int32)
+            rst = np.ascontiguousarray(view.recv_start, dtype=np.int64)
+            rct = np.ascontiguousarray(view.recv_count, dtype=np.int64)
+            uid = (C.c_char * 128).from_buffer_copy(bytes(nccl_uid)) if nccl_uid is not None else None
+            st = self.lib.amaru_create_partitioned(
+                int(flat["ndim"]), int(flat["stressmodel"]), float(flat["thickness"]), coords.shape[0], int(view.nowned),
+                _d(coords), len(bshape), bshape.ctypes.data_as(_i32p), bnelem.ctypes.data_as(_i64p),
+                conn.ctypes.data_as(_i32p), emat.ctypes.data_as(_i32p), len(mkind), mkind.ctypes.data_as(_i32p), _d(mpar),
+                eq.ctypes.data_as(_i32p), self.ndofs, self.nu, int(view.rank), int(view.nranks), len(neigh),
+                neigh.ctypes.data_as(_i32p), sptr.ctypes.data_as(_i64p), snod.ctypes.data_as(_i32p),
+                rst.ctypes.data_as(_i64p), rct.ctypes.data_as(_i64p), C.cast(uid, _vp) if uid is not None else None,
+                int(device), C.byref(h), self._msg, len(self._msg))
         if st != OK:
             raise AmaruStatus(st, self._msg.value.decode(errors="replace"))
         self.h = h

@@ -95,19 +95,22 @@ int amaru_create(int ndim, int stressmodel, double thickness,
                  const int32_t *eqid, int64_t ndofs, int64_t nu,
                  int device, amaru_model **out, char *msg, int msglen);
 
-/* Multi-GPU variant: this rank owns `nowned` nodes (local ids 0..nowned-1, the rest are ghosts) and
- * passes its own + halo elements; `node_gid[nnodes]` are global node ids used to match ghosts with
- * their owners; `nccl_uid` is the 128-byte ncclUniqueId shared by all ranks.  eqid is global. */
+/* Multi-GPU variant (one process per GPU; the reference has no distributed path).  This rank passes its
+ * LOCAL view of the partitioned mesh: `nnodes` local nodes of which the first `nowned` are owned (the rest are ghosts,
+ * grouped by owner rank), its own + halo elements (every element touching an owned node) with local node ids, and
+ * `eqid` = GLOBAL eq ids of the local nodes (ndofs / nu are the global numbers; ABI vectors stay global-length).
+ * Halo lists: for neighbour q = neigh_rank[i], send the owned local nodes send_nodes[send_ptr[i] .. send_ptr[i+1]) and
+ * receive recv_count[i] ghosts into local nodes [recv_start[i], ...); both sides order the nodes by global id.
+ * `nccl_uid` is the 128-byte ncclUniqueId made on rank 0 by amaru_nccl_unique_id and broadcast by the host. */
 int amaru_create_partitioned(int ndim, int stressmodel, double thickness,
-                             int64_t nnodes, int64_t nowned, const double *coords, const int64_t *node_gid,
-                             const int32_t *node_owner,
+                             int64_t nnodes, int64_t nowned, const double *coords,
                              int nbatches, const int32_t *batch_shape, const int64_t *batch_nelem,
-                             const int32_t *conn, const int32_t *elem_mat, const uint8_t *elem_owned,
+                             const int32_t *conn, const int32_t *elem_mat,
                              int nmats, const int32_t *mat_kind, const double *mat_params,
-                             const int32_t *eqid_local, const uint8_t *dof_prescribed,
-                             int64_t ndofs_global, int64_t nu_global,
-                             int rank, int nranks, const void *nccl_uid,
-                             int device, amaru_model **out, char *msg, int msglen);
+                             const int32_t *eqid, int64_t ndofs, int64_t nu,
+                             int rank, int nranks, int nneigh, const int32_t *neigh_rank, const int64_t *send_ptr,
+                             const int32_t *send_nodes, const int64_t *recv_start, const int64_t *recv_count,
+                             const void *nccl_uid, int device, amaru_model **out, char *msg, int msglen);
 int amaru_nccl_unique_id(void *uid128, char *msg, int msglen);
 
 int amaru_destroy(amaru_model *m);
