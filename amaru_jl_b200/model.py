@@ -185,10 +185,21 @@ class FEModel:
         nd = self.ndim
         self.U = np.zeros((self.nnodes, nd))
         self.F = np.zeros((self.nnodes, nd))
-        self.state = dict(sigma=np.zeros((self.nip_total, 6)), eps=np.zeros((self.nip_total, 6)),
-                          epa=np.zeros(self.nip_total), dlam=np.zeros(self.nip_total))
+        self._state = None                                           # allocated on first use (3.6 GB at 8 M HEX20 elements)
         self.ndofs = self.nnodes * nd
         self._ipcoords = None
+
+    @property
+    def state(self):
+        """ip.state of every IP, element-major: zero-initialised like the IpState constructors (von-mises.jl:35-42)."""
+        if self._state is None:
+            self._state = dict(sigma=np.zeros((self.nip_total, 6)), eps=np.zeros((self.nip_total, 6)),
+                               epa=np.zeros(self.nip_total), dlam=np.zeros(self.nip_total))
+        return self._state
+
+    @state.setter
+    def state(self, value):
+        self._state = value
 
     def _select_elems(self, flt):
         if isinstance(flt, str):

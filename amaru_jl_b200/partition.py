@@ -60,7 +60,8 @@ def partition_mesh(coords: np.ndarray, conn: np.ndarray, nranks: int, rank: int,
         elem_part = rcb_partition(cent, nranks)
     elem_part = np.asarray(elem_part, dtype=np.int32)
     owner = np.full(nnodes, np.iinfo(np.int32).max, dtype=np.int32)
-    np.minimum.at(owner, conn.reshape(-1), np.repeat(elem_part, nn))
+    for p in range(int(nranks) - 1, -1, -1):                       # lowest part touching a node wins (assigned last)
+        owner[conn[elem_part == p].reshape(-1)] = p
     eown = owner[conn]                                              # (nelem, nn) owners of the element's nodes
     v = LocalView()
     v.rank, v.nranks = rank, nranks

@@ -1,19 +1,22 @@
 #!/usr/bin/env python
 """bench.py — elements/s per Newton iteration (assembly + PCG + state update) of the mechanical hot path.
 
-Workload (BASELINE.json configs[2], the configuration the metric's target is quoted on): HEX20 n^3 block on [0,1]^3
-(n=100 -> 1 M elements, 12.27 M dofs), von Mises E=210e6 nu=0.3 fy=240e3 H=0, z=0 clamped, rigid footing = prescribed
-uz on the patch x,y in [0.4,0.6] of z=1, ten equal load increments.  A "step" is ONE Newton iteration
-of the first increment: mount_K on the plastic trial state -> solve_system! (PCG to cg_rtol) -> state restore ->
-update_state!.  Every timed step does identical work (each restarts from the converged state, mech-solver.jl:333).
+Workload (BASELINE.json configs[2], the configuration the metric's target is quoted on): HEX20 block, n^3 elements per
+GPU (n=100 -> 1 M elements, 12.27 M dofs per GPU), von Mises E=210e6 nu=0.3 fy=240e3 H=0, bottom clamped, rigid footing
+= prescribed uz on a 0.2 x 0.2 patch in the middle of the top face, ten equal load increments.  A "step"
+is ONE Newton iteration of the first increment: mount_K on the plastic trial state -> solve_system! (PCG to cg_rtol) ->
+state restore -> update_state!.  Every timed step does identical work (each restarts from the converged state,
+mech-solver.jl:333).
 
-  value  : device-timed (CUDA events on the library's stream), vectors resident in HBM
-  e2e    : the same iteration through the C ABI with HOST buffers (pinned), H2D/D2H copies inside the timed region
+  value   : device-timed (CUDA events on the library's stream), vectors resident in HBM; whole job = all ranks' elements
+  e2e     : the same iteration through the C ABI with HOST buffers (pinned), H2D/D2H copies inside the timed region
   roofline: the dominant kernel (block-CSR SpMV of the PCG), algorithmic bytes / live CUDA-event duration
   cpu_baseline: the CPU oracle (restated reference path: COO assembly -> sparse -> direct LU -> state update) on a
-           bounded sample (rank 0, N=1 only)
+            bounded sample (rank 0, N=1 only)
 
-`--impl reference` times that CPU path alone.  Multi-GPU (torchrun): weak scaling, the block grows along z with N.
+`--impl reference` times that CPU path alone.  Multi-GPU (torchrun, one rank per GPU): weak scaling — the block grows to
+(Nx*n, Ny*n, Nz*n) elements with Nx*Ny*Nz = N as cubic as possible, partitioned by recursive coordinate bisection with
+duplicated halo elements; the PCG exchanges halo entries of p and two small all-reduces per iteration over NCCL.
 """
 from __future__ import annotations
 
@@ -33,15 +36,17 @@ if ROOT not in sys.path:
 
 METRIC = "elements/sec per Newton iteration (assembly+PCG)"
 UNIT = "elements/s"
+GRID = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}
 
 
-def footing_model(n, nz=None, z0=0.0, z1=1.0):
+def footing_model(n, mult=(1, 1, 1)):
     from amaru_jl_b200 import Block, FEModel, MechContext, MechSolid, Mesh, NodeBC, VonMises
-    nz = nz or n
-    mesh = Mesh(Block([[0, 0, z0], [1, 1, z1]], nx=n, ny=n, nz=nz, cellshape="HEX20", tag="solids"))
+    mx, my, mz = mult
+    mesh = Mesh(Block([[0, 0, 0], [mx, my, mz]], nx=n * mx, ny=n * my, nz=n * mz, cellshape="HEX20", tag="solids"))
     model = FEModel(mesh, [("solids", MechSolid, VonMises, dict(E=210e6, nu=0.3, fy=240e3, H=0.0))], MechContext())
-    bcs = [(f"z=={z0}", NodeBC(ux=0, uy=0, uz=0)),
-           (f"z=={z1} and x>=0.4 and x<=0.6 and y>=0.4 and y<=0.6", NodeBC(uz=-0.01))]
+    cx, cy = mx / 2.0, my / 2.0
+    bcs = [("z==0", NodeBC(ux=0, uy=0, uz=0)),
+           (f"z=={mz} and x>={cx - 0.1} and x<={cx + 0.1} and y>={cy - 0.1} and y<={cy + 0.1}", NodeBC(uz=-0.01))]
     return model, bcs
 
 
@@ -127,12 +132,13 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--size", type=int, default=100, help="elements per side of the HEX20 block (100 -> 1 M elements)")
+    ap.add_argument("--size", type=int, default=100, help="HEX20 elements per side PER GPU (100 -> 1 M elements per GPU)")
     ap.add_argument("--cpu-size", type=int, default=12, help="elements per side of the CPU baseline sample")
     ap.add_argument("--cg-rtol", type=float, default=1e-10)
     ap.add_argument("--cg-maxit", type=int, default=200000)
     ap.add_argument("--precond", default="block-jacobi", choices=["jacobi", "block-jacobi"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -151,17 +157,26 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-        if world > 1 and not hasattr(L, "PartitionedModel"):
-            raise SystemExit("multi-GPU path not built")
 
     pc = L.PRECOND[args.precond]
     n = args.size
+    mult = GRID.get(world, (world, 1, 1))
     t_setup = time.perf_counter()
-    model, bcs = footing_model(n)
+    model, bcs = footing_model(n, mult)
     eqid, nu, setup = model.configure_dofs(bcs)
     Uex, Fex = model.get_bc_vals(eqid, setup)
     ndofs = int(eqid.size)
-    dm = L.DeviceModel(model.flatten(), eqid, ndofs, nu, device=local_rank)
+    if world == 1:
+        dm = L.DeviceModel(model.flatten(), eqid, ndofs, nu, device=local_rank)
+        nlocal_elems, nlocal_nodes = model.nelems, model.nnodes
+    else:
+        from amaru_jl_b200.partition import local_flat, partition_mesh
+        view = partition_mesh(model.coords, model.conn, world, rank)
+        lf, eql = local_flat(model.flatten(), eqid, view)
+        uid = [L.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        dm = L.DeviceModel(lf, eql, ndofs, nu, device=local_rank, view=view, nccl_uid=uid[0])
+        nlocal_elems, nlocal_nodes = int(view.elem_gid.size), int(view.node_gid.size)
     t_setup = time.perf_counter() - t_setup
     dUex, dFex = 0.1 * Uex, 0.1 * Fex                      # first of ten equal increments
     dm.state_backup()
@@ -173,7 +188,6 @@ def main():
         torch.cuda.synchronize()
 
     # ---- warm-up: the first pass assembles the elastic K; later passes run on the plastic trial state
-    launches0 = dm.launches
     for _ in range(max(args.warmup, 3)):
         info = dm.newton_iteration_device(args.cg_rtol, args.cg_maxit, pc)
     # ---- timed region (device-resident)
@@ -195,34 +209,36 @@ def main():
     dm.set_profiling(False)
 
     # ---- e2e: the reference-facing C-ABI calls with pinned HOST buffers, copies inside the timed region
-    hU = torch.empty(ndofs, dtype=torch.float64).pin_memory().numpy()
-    hF = torch.empty(ndofs, dtype=torch.float64).pin_memory().numpy()
-    hdF = torch.empty(ndofs, dtype=torch.float64).pin_memory().numpy()
-    barrier()
-    e0 = time.perf_counter()
-    for _ in range(args.steps):
-        hU[:] = dUex
-        hF[:] = dFex
-        dm.assemble_K()
-        dm.solve(hU, hF, args.cg_rtol, args.cg_maxit, pc)
-        dm.state_restore()
-        dm.update_state(hU, hdF)
-        resid = float(np.abs(hF[:nu] - hdF[:nu]).max())       # the Newton residual read back on the host
-    barrier()
-    e2e_s = time.perf_counter() - e0
+    e2e_s, resid = None, None
+    if not args.no_e2e:
+        hU = torch.empty(ndofs, dtype=torch.float64).pin_memory().numpy()
+        hF = torch.empty(ndofs, dtype=torch.float64).pin_memory().numpy()
+        hdF = torch.empty(ndofs, dtype=torch.float64).pin_memory().numpy()
+        barrier()
+        e0 = time.perf_counter()
+        for _ in range(args.steps):
+            hU[:] = dUex
+            hF[:] = dFex
+            dm.assemble_K()
+            dm.solve(hU, hF, args.cg_rtol, args.cg_maxit, pc)
+            dm.state_restore()
+            dm.update_state(hU, hdF)
+            resid = float(np.abs(hF[:nu] - hdF[:nu]).max())   # the Newton residual read back on the host
+        barrier()
+        e2e_s = time.perf_counter() - e0
     sampler.stop_flag = True
     sampler.join(timeout=2)
 
     t_dev = dev_ms / 1e3
     if dist is not None:
-        tt = torch.tensor([t_dev, e2e_s], dtype=torch.float64, device="cuda")
+        tt = torch.tensor([t_dev, e2e_s or 0.0], dtype=torch.float64, device="cuda")
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        t_dev, e2e_s = float(tt[0]), float(tt[1])
-    nelem_total = model.nelems * world
+        t_dev, e2e_max = float(tt[0]), float(tt[1])
+        e2e_s = e2e_max if e2e_s is not None else None
+    nelem_total = model.nelems
     value = nelem_total * args.steps / t_dev
-    e2e_val = nelem_total * args.steps / e2e_s
 
-    # ---- roofline of the dominant kernel (SpMV): algorithmic bytes per launch / average live duration
+    # ---- roofline of the dominant kernel (SpMV): algorithmic bytes per launch / average live duration (this rank)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -230,38 +246,44 @@ def main():
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     nd = model.ndim
-    nblk, nrows, nloc = dm.nblocks, model.nnodes, ndofs
+    nblk = dm.nblocks
+    nloc = nlocal_nodes * nd
     spmv_bytes = int(dm.spmv_bytes)   # values + tile records of the stored format + x once + y once
     avg_spmv_ms = spmv_ms / max(spmv_n, 1)
     achieved = spmv_bytes / (avg_spmv_ms * 1e-3) / 1e9 if spmv_n else None
     cg_iters = [p["cg_iters"] for p in phases]
-    # whole-iteration algorithmic bytes: assembly + update + iters * cg
+    # whole-iteration algorithmic bytes of this rank
     S = 14
-    nip = model.nip_total
-    b_cg = spmv_bytes + nloc * (5 * 8 + 3 * 8 + nd * 8) + nloc * 3 * 8
-    b_asm = model.nelems * 20 * 4 + 8 * 3 * model.nnodes + nip * 8 * 7 + 8 * nblk * nd * nd
-    b_upd = model.nelems * 20 * 4 + 2 * 8 * 3 * model.nnodes + 2 * nip * 8 * S + 8 * nloc
+    nip = nlocal_elems * model.nip
+    b_cg = spmv_bytes + nloc * (104 + 24)
+    b_asm = nlocal_elems * 20 * 4 + 24 * nlocal_nodes + nip * 56 + nlocal_elems * 400 * 4 + 8 * nblk * nd * nd
+    b_upd = nlocal_elems * 20 * 4 + 48 * nlocal_nodes + 2 * nip * 8 * S + 8 * nloc
     b_it = b_asm + b_upd + float(np.mean(cg_iters)) * b_cg + 2 * nip * 8 * S
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"configs[2]: HEX20 {n}^3 von Mises footing, one Newton iteration per step", "elements": nelem_total,
-                   "dofs": ndofs * world, "nnz": int(dm.nnz), "cg_rtol": args.cg_rtol, "precond": args.precond,
-                   "cg_iters_per_step": cg_iters, "l2": "inputs (K = %.1f GB) larger than L2" % (dm.nnz * 8 / 1e9),
-                   "parallelism": f"dd{world}", "setup_s": round(t_setup, 2)},
+        "config": {"workload": f"configs[2]: HEX20 von Mises footing, {n}^3 elements per GPU, block {mult[0]}x{mult[1]}x{mult[2]}, "
+                               "one Newton iteration per step", "elements": nelem_total, "dofs": ndofs, "nnz_rank0": int(dm.nnz),
+                   "cg_rtol": args.cg_rtol, "precond": args.precond, "cg_iters_per_step": cg_iters,
+                   "l2": "inputs (K = %.1f GB per GPU) larger than L2" % (dm.nnz * 8 / 1e9),
+                   "parallelism": f"dd{world} (element partition + halo elements, NCCL halo exchange)" if world > 1 else "dd1",
+                   "setup_s": round(t_setup, 2)},
         "phases_ms": {k: float(np.mean([p[k] for p in phases])) for k in ("assemble_ms", "solve_ms", "update_ms")},
-        "iteration_gbs": b_it / (t_dev / args.steps) / 1e9,
+        "ms_per_cg_iteration": float(np.mean([p["solve_ms"] / max(p["cg_iters"], 1) for p in phases])),
+        "iteration_gbs_rank0": b_it / (t_dev / args.steps) / 1e9,
         "wall_s_timed_region": wall_s,
         "gpu_launches": int(gpu_launches),
         "clocks": sampler.summary(),
-        "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": 3 * ndofs * 8, "d2h_bytes_per_step": 3 * ndofs * 8,
-                "newton_residual": resid},
-        "roofline": {"bound": "hbm", "kernel": "k_spmv<3,true> (block-CSR SpMV + p.Ap dot)", "achieved": achieved, "peak": peak,
-                     "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "traffic": None,
-                     "bytes_per_launch": spmv_bytes, "avg_launch_ms": avg_spmv_ms, "launches_timed": int(spmv_n),
+        "roofline": {"bound": "hbm", "kernel": "k_spmv_stream<3,true> (TMA-streamed block-CSR SpMV + p.Ap dot), rank 0",
+                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
+                     "traffic": None, "bytes_per_launch": spmv_bytes, "avg_launch_ms": avg_spmv_ms,
+                     "launches_timed": int(spmv_n),
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)"},
     }
+    if e2e_s is not None:
+        line["e2e"] = {"value": nelem_total * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 3 * ndofs * 8,
+                       "d2h_bytes_per_step": 3 * ndofs * 8, "newton_residual": resid}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         val, cores, t, inf = cpu_reference_step(args.cpu_size, steps=1, warmup=0)
         line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
