@@ -244,7 +244,7 @@ void free_model(amaru_model *m) {
         cudaFree(B.d_conn); cudaFree(B.d_emat); cudaFree(B.d_map); cudaFree(B.d_perm); cudaFree(B.d_owned);
         cudaFree(B.d_rho); cudaFree(B.d_dNdR); cudaFree(B.d_N); cudaFree(B.d_w);
     }
-    if (m->d_A && m->d_A != m->d_K) cudaFree(m->d_A);
+    cudaFree(m->d_Abuf);
     for (void *p : {(void *)m->d_coords, (void *)m->d_eqid, (void *)m->d_fixed, (void *)m->d_mat_kind, (void *)m->d_mat_par,
                     (void *)m->d_rowptr, (void *)m->d_col, (void *)m->d_diag, (void *)m->d_K, (void *)m->d_M,
                     (void *)m->d_Minv, (void *)m->d_state, (void *)m->d_statebk, (void *)m->d_x, (void *)m->d_r,

@@ -101,6 +101,7 @@ struct amaru_model {
     double *d_K = nullptr;         // [nblk*nd*nd]
     double *d_M = nullptr;         // mass, same pattern (next tier)
     double *d_A = nullptr;         // a*K+b*M when a system matrix is set, else == d_K
+    double *d_Abuf = nullptr;      // storage behind d_A when it is not d_K
     double sysA = 1.0, sysB = 0.0;
     double *d_Minv = nullptr;      // block-Jacobi inverses [nowned*nd*nd] or Jacobi [nowned*nd]
     int minv_kind = -1;            // which preconditioner d_Minv currently holds (-1 = stale)

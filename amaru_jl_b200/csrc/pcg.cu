@@ -442,7 +442,8 @@ void amaru_combine_matrix(amaru_model *m) {
         m->d_A = m->d_K;
     } else {
         AMARU_REQUIRE(m->d_M != nullptr, AMARU_ERR_ARG, "set_system_matrix: mass matrix not assembled");
-        if (m->d_A == m->d_K || m->d_A == nullptr) CUDA_CHECK(cudaMalloc(&m->d_A, (size_t)n * sizeof(double) + 256));
+        if (!m->d_Abuf) CUDA_CHECK(cudaMalloc(&m->d_Abuf, (size_t)n * sizeof(double) + 256));
+        m->d_A = m->d_Abuf;
         k_axpby_matrix<<<blocks_for(m, n, 256), 256, 0, m->stream>>>(n, m->sysA, m->d_K, m->sysB, m->d_M, m->d_A);
         m->launches++;
         CUDA_CHECK(cudaGetLastError());
