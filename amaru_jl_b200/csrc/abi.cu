@@ -569,20 +569,24 @@ int amaru_matvec(amaru_model *m, double a, double b, const double *x, double *y,
     return guarded(msg, msglen, [&]() {
         AMARU_REQUIRE(m && x && y, AMARU_ERR_ARG, "null argument");
         use_device(m);
-        const double sa = m->sysA, sb = m->sysB;
-        const int kind = m->minv_kind;
-        m->sysA = a; m->sysB = b;
-        amaru_combine_matrix(m);
+        AMARU_REQUIRE(b == 0.0 || m->d_M != nullptr, AMARU_ERR_ARG, "amaru_matvec: mass matrix not assembled");
+        // y = a*(K x) + b*(M x): two products on the stored matrices, no combined matrix is formed
         const size_t bytes = (size_t)m->ndofs * sizeof(double);
         CUDA_CHECK(cudaMemcpyAsync(m->d_U, x, bytes, cudaMemcpyHostToDevice, m->stream));
         amaru_eq_to_nodes(m, m->d_U, m->d_x);
-        amaru_spmv(m, m->d_A, m->d_x, m->d_q, 0);
-        amaru_nodes_to_eq(m, m->d_q, m->d_F, 0);
+        if (m->nranks > 1) amaru_halo_exchange(m, m->d_x);
+        amaru_spmv(m, m->d_K, m->d_x, m->d_q, 0);
+        if (b != 0.0) amaru_spmv(m, m->d_M, m->d_x, m->d_r, 0);
+        amaru_axpby(m, m->nowned * m->nd, a, m->d_q, b, b != 0.0 ? m->d_r : m->d_q, m->d_q);
+        if (m->nranks == 1) {
+            amaru_nodes_to_eq(m, m->d_q, m->d_F, 0);
+        } else {
+            CUDA_CHECK(cudaMemsetAsync(m->d_F, 0, bytes, m->stream));
+            amaru_nodes_to_eq(m, m->d_q, m->d_F, 0);
+            amaru_allreduce_sum(m, m->d_F, m->ndofs);
+        }
         CUDA_CHECK(cudaMemcpyAsync(y, m->d_F, bytes, cudaMemcpyDeviceToHost, m->stream));
         CUDA_CHECK(cudaStreamSynchronize(m->stream));
-        m->sysA = sa; m->sysB = sb;
-        amaru_combine_matrix(m);
-        (void)kind;
         return AMARU_OK;
     });
 }

@@ -169,6 +169,7 @@ void amaru_nodes_to_eq(amaru_model *m, const double *d_nodes, double *d_eq, int 
 void amaru_combine_matrix(amaru_model *m);                            // pcg.cu: d_A = a*K + b*M
 int amaru_check_nan(amaru_model *m, const double *d_v, int64_t n);    // pcg.cu
 void amaru_zero_free(amaru_model *m, double *x);                     // pcg.cu
+void amaru_axpby(amaru_model *m, int64_t n, double a, const double *x, double b, const double *y, double *out);  // pcg.cu
 void amaru_time_cg_kernel(amaru_model *m, int kind, int precond, int reps);  // pcg.cu
 
 // halo exchange (halo.cu) — no-ops for nranks == 1

@@ -213,8 +213,7 @@ __global__ void k_nodes_to_eq(int64_t n, const int32_t *__restrict__ eqid, const
         if (which == 0 || (which == 1 && !fx) || (which == 2 && fx)) dst[eqid[i]] = src[i];
     }
 }
-__global__ void k_axpby_matrix(int64_t n, double a, const double *__restrict__ K, double b, const double *__restrict__ M,
-                               double *A) {
+__global__ void k_axpby_matrix(int64_t n, double a, const double *K, double b, const double *M, double *A) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
         A[i] = a * K[i] + b * M[i];
 }
@@ -432,6 +431,14 @@ void amaru_eq_to_nodes(amaru_model *m, const double *d_eq, double *d_nodes) {
 void amaru_nodes_to_eq(amaru_model *m, const double *d_nodes, double *d_eq, int which) {
     const int64_t n = m->nowned * m->nd;   // only rows this rank owns
     k_nodes_to_eq<<<blocks_for(m, n, 256), 256, 0, m->stream>>>(n, m->d_eqid, m->d_fixed, d_nodes, d_eq, which);
+    m->launches++;
+    CUDA_CHECK(cudaGetLastError());
+}
+
+// out = a*x + b*y (elementwise; out may alias x or y)
+void amaru_axpby(amaru_model *m, int64_t n, double a, const double *x, double b, const double *y, double *out) {
+    if (n <= 0) return;
+    k_axpby_matrix<<<blocks_for(m, n, 256), 256, 0, m->stream>>>(n, a, x, b, y, out);
     m->launches++;
     CUDA_CHECK(cudaGetLastError());
 }

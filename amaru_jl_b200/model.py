@@ -170,8 +170,16 @@ class FEModel:
             par = bind[3] if len(bind) > 3 else {}
             if not (ety is MechSolid or isinstance(ety, MechSolid)):
                 raise AmaruError("only MechSolid elements are on the B200 hot path (no CPU fallback)")
-            props = ety if isinstance(ety, MechSolid) else MechSolid()
-            mat = mty if isinstance(mty, Material) else mty(**dict(par))
+            par = dict(par)
+            # `rho` / `gamma` in the parameter tuple are element properties (mech-solid.jl:13-28); materials that also
+            # declare rho (VonMises, DruckerPrager) receive it too, like the reference's shared kwarg list
+            eprops = {k: par[k] for k in ("rho", "gamma") if k in par}
+            props = ety if isinstance(ety, MechSolid) else MechSolid(**eprops)
+            if not isinstance(mty, Material):
+                import inspect
+                accepted = inspect.signature(mty.__init__).parameters
+                par = {k: v for k, v in par.items() if k in accepted}
+            mat = mty if isinstance(mty, Material) else mty(**par)
             if not isinstance(mat, (LinearElastic, VonMises, DruckerPrager)):
                 raise AmaruError("only LinearElastic, VonMises, DruckerPrager are on the B200 hot path")
             sel = self._select_elems(flt)
@@ -368,8 +376,9 @@ class FEModel:
 
 # ------------------------------------------------------------------------------------------ analysis / stages
 class Stage:
-    def __init__(self, sid, bcs, nincs=1, nouts=0):
+    def __init__(self, sid, bcs, nincs=1, nouts=0, tspan=0.0):
         self.id, self.bcs, self.nincs, self.nouts = sid, list(bcs), int(nincs), int(nouts)
+        self.tspan = float(tspan)
         self.status = "pending"
 
 
@@ -405,8 +414,22 @@ class MechAnalysis:
         self.stats: list[dict] = []            # per Newton iteration: cg iterations, residue, timings
 
 
-def addstage(ana: MechAnalysis, bcs, nincs=1, nouts=0):
-    """addstage!(ana, bcs; nincs, nouts) (analysis.jl:27-31)."""
-    st = Stage(len(ana.stages) + 1, bcs, nincs, nouts)
+class DynamicAnalysis(MechAnalysis):
+    """DynamicAnalysis(model) (src/mech/dyn-solver.jl:35-66): Newmark time integration; stages carry `tspan`."""
+
+    def __init__(self, model: FEModel, outdir=".", outkey="out"):
+        super().__init__(model, outdir, outkey)
+        self.t = 0.0
+        nd = model.ndim
+        model.V = np.zeros((model.nnodes, nd))       # dof.vals[:vx..]
+        model.A = np.zeros((model.nnodes, nd))       # dof.vals[:ax..]
+
+
+DynAnalysis = DynamicAnalysis
+
+
+def addstage(ana: MechAnalysis, bcs, nincs=1, nouts=0, tspan=0.0):
+    """addstage!(ana, bcs; nincs, nouts, tspan) (analysis.jl:27-31)."""
+    st = Stage(len(ana.stages) + 1, bcs, nincs, nouts, tspan)
     ana.stages.append(st)
     return st
