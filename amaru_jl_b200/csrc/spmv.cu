@@ -8,14 +8,15 @@
 //   contiguous in block-CSR, so a tile is ONE contiguous byte range of the value array.  Per tile the host also
 //   builds one packed record: one int per row (local block offset | prescribed-dof mask << 16 | local index of the
 //   diagonal << 19), the sorted list of unique column nodes `ucol`, and a 16-bit tile-local column index per block.
-//   Each CTA = 1 producer warp + NCW consumer warps.  The producer keeps `nstages` tiles in flight in shared memory
-//   (two bulk copies per tile — values and record — with an L2 evict_first policy so that x stays L2-resident; tile
-//   headers are prefetched 32 tiles ahead), paced by empty/full mbarriers.  The consumers start the gather of the x
-//   entries of tile i+xd with cp.async (8-byte copies, nothing held in registers) and contract tile i entirely out of
-//   shared memory with the 27-lane (3x3) / 32-lane (2x2) slot mapping.  No global load sits on the critical path of
-//   the inner loop; bytes in flight are decoupled from registers and occupancy.
-//   (profiles/tma_stream_bench.cu: one CTA sustains ~2 bulk-copy phases per microsecond whatever the copy size, so a
-//   tile must carry >= ~12 KB per resident CTA to reach the 7.3 TB/s read rate of this B200.)
+//   Each CTA = 1 producer warp + NCW consumer warps.  The producer streams the values of `nstages` tiles and the
+//   records of `nstages + xd` tiles through two shared-memory rings (two bulk copies per tile with an L2 evict_first
+//   policy so that x stays L2-resident; tile headers are prefetched 32 tiles ahead), paced by empty/full mbarriers.
+//   The consumers start the gather of the x entries of tile i+xd with cp.async (8-byte copies, nothing held in
+//   registers) and contract tile i entirely out of shared memory: lane = (block-in-step, row), so one warp step
+//   covers 10 (3x3) / 16 (2x2) blocks.  No global load sits on the critical path of the inner loop; bytes in flight
+//   are decoupled from registers and occupancy.
+//   (profiles/tma_stream_bench.cu: pure bulk-copy streaming reads 7.3 TB/s on this B200; profiles/README.md: the
+//   kernel's DRAM traffic equals its algorithmic bytes, what is left is consumer instruction issue.)
 // k_spmv (fallback when a single row exceeds a tile, or AMARU_SPMV_SIMPLE=1) — one warp per block row, per-lane loads.
 //
 // Algorithmic bytes per launch: nblk*(8*bs^2 + 2) + 4*(rows + 1 + unique columns) per tile + 32 per tile
@@ -31,7 +32,7 @@ namespace {
 
 constexpr int ROW_THREADS = 256;
 constexpr int MAX_STAGES = 8;
-constexpr int NCW = 4;                      // consumer warps per CTA
+constexpr int NCW = 4;                      // consumer warps per CTA (8 with 2x larger tiles measured the same: 3.11 ms)
 constexpr int STREAM_THREADS = (NCW + 1) * 32;
 constexpr int XD_MAX = 4;                   // x gathers are started xd (<= XD_MAX) tiles ahead of the contraction
 
@@ -59,7 +60,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
 }
 // producer-side wait: sleeps between probes so that the spinning warp does not steal issue slots from the consumer
 // warp that shares its scheduler (ncu: the bare try_wait loop executed 4x more instructions than the contraction)
-__device__ __forceinline__ void mbar_wait_backoff(uint64_t *bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t *bar, uint32_t parity, unsigned sleep_ns) {
     uint32_t done = 0;
     while (true) {
         asm volatile(
@@ -69,7 +70,7 @@ __device__ __forceinline__ void mbar_wait_backoff(uint64_t *bar, uint32_t parity
             "selp.u32 %0, 1, 0, P1;\n"
             "}" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
         if (done) break;
-        __nanosleep(100);
+        __nanosleep(sleep_ns);
     }
 }
 __device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar, uint64_t policy) {
@@ -129,8 +130,8 @@ template <int BS, bool DOT>
 __global__ void __launch_bounds__(STREAM_THREADS)
 k_spmv_stream(int ntiles, const SpmvTile *__restrict__ tiles, const int32_t *__restrict__ trec,
               const double *__restrict__ A, const double *__restrict__ x, double *__restrict__ y, int mask_rows,
-              int tile_blks, int tile_rows, int xcap, int nstages, int XD, double *partial, CgScalars *scal,
-              int check_done, int finalize) {
+              int tile_blks, int tile_rows, int xcap, int nstages, int XD, int sleep_ns, double *partial,
+              CgScalars *scal, int check_done, int finalize) {
     if (check_done && scal->done) return;
     constexpr int B2 = BS * BS, BPI = 32 / B2, ACT = BPI * B2, NCT = NCW * 32;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -189,7 +190,7 @@ k_spmv_stream(int ntiles, const SpmvTile *__restrict__ tiles, const int32_t *__r
                 }
                 if (lane == 0) {
                     const int sr = psr;
-                    if (j >= SR) mbar_wait_backoff(&empty_r[sr], prph);
+                    if (j >= SR) mbar_wait_backoff(&empty_r[sr], prph, (unsigned)sleep_ns);
                     shdr[sr] = ti;
                     const uint64_t rs = ((uint64_t)ti.recints * 4 + 15) & ~15ull;
                     mbar_arrive_expect_tx(&full_r[sr], (uint32_t)rs);
@@ -206,7 +207,7 @@ k_spmv_stream(int ntiles, const SpmvTile *__restrict__ tiles, const int32_t *__r
             const int b0 = __shfl_sync(0xffffffffu, vb0, jv & 31), nb = __shfl_sync(0xffffffffu, vnb, jv & 31);
             if (jv >= 0 && lane == 0) {
                 const int sv = psv;
-                if (jv >= SV) mbar_wait_backoff(&empty_v[sv], pvph);
+                if (jv >= SV) mbar_wait_backoff(&empty_v[sv], pvph, (unsigned)sleep_ns);
                 const uint64_t v0 = (uint64_t)b0 * (B2 * 8), va = v0 & ~15ull;
                 const uint64_t vs = ((v0 + (uint64_t)nb * (B2 * 8) - va) + 15) & ~15ull;
                 mbar_arrive_expect_tx(&full_v[sv], (uint32_t)vs);
@@ -403,7 +404,7 @@ void launch_stream(amaru_model *m, const double *A, const double *x, double *y, 
     const size_t smem = m->spmv_stages * L.vbytes + (size_t)(m->spmv_stages + m->spmv_xd) * (L.rbytes + L.xbytes);
     k_spmv_stream<BS, DOT><<<m->grid_tma, STREAM_THREADS, smem, m->stream>>>(
         m->ntiles, reinterpret_cast<const SpmvTile *>(m->d_tiles), m->d_tmeta, A, x, y, mask, m->tile_blks, m->tile_rows,
-        m->tile_xcap, m->spmv_stages, m->spmv_xd, m->d_partial, m->d_scal, check_done, finalize);
+        m->tile_xcap, m->spmv_stages, m->spmv_xd, m->spmv_sleep, m->d_partial, m->d_scal, check_done, finalize);
 }
 
 template <int BS>
@@ -447,6 +448,7 @@ void amaru_spmv_setup(amaru_model *m) {
     m->tile_blks = std::min(env_int("AMARU_SPMV_TILE", bs == 3 ? 232 : 522), 8191);   // 13-bit local diagonal index
     if ((int64_t)m->tile_blks * bs > 65535) m->tile_blks = 65535 / bs;   // lcol holds (local column)*bs in 16 bits
     m->tile_rows = env_int("AMARU_SPMV_TILE_ROWS", 32);
+    m->spmv_sleep = env_int("AMARU_SPMV_SLEEP", 100);   // ns between probes of the producer's empty-barrier wait
 
     const std::vector<int32_t> &rp = m->h_rowptr, &cl = m->h_col;
     std::vector<SpmvTile> tiles;

@@ -1,11 +1,7 @@
 #!/bin/bash
 SIZE=${1:-100}
 run() { echo -n "$* : "; env "$@" timeout 300 python profiles/prof_kernels.py --size $SIZE 2>&1 | grep "spmv" || echo failed; }
-run AMARU_SPMV_STAGES=2 AMARU_SPMV_TILE=256 AMARU_SPMV_XD=2
-run AMARU_SPMV_STAGES=2 AMARU_SPMV_TILE=256 AMARU_SPMV_XD=1
-run AMARU_SPMV_STAGES=2 AMARU_SPMV_TILE=232 AMARU_SPMV_XD=1
-run AMARU_SPMV_STAGES=2 AMARU_SPMV_TILE=232 AMARU_SPMV_XD=2
-run AMARU_SPMV_STAGES=2 AMARU_SPMV_TILE=288 AMARU_SPMV_XD=2
-run AMARU_SPMV_STAGES=2 AMARU_SPMV_TILE=324 AMARU_SPMV_XD=2
-run AMARU_SPMV_STAGES=2 AMARU_SPMV_TILE=324 AMARU_SPMV_XD=1
-run AMARU_SPMV_STAGES=2 AMARU_SPMV_TILE=208 AMARU_SPMV_XD=1
+run AMARU_SPMV_SLEEP=100
+run AMARU_SPMV_SLEEP=20
+run AMARU_SPMV_SLEEP=300
+run AMARU_SPMV_SLEEP=800
