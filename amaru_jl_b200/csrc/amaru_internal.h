@@ -126,7 +126,7 @@ struct amaru_model {
     // streamed SpMV (spmv.cu): row tiles, per-tile records, launch geometry
     void *d_tiles = nullptr;       // SpmvTile[ntiles]
     int32_t *d_tmeta = nullptr;    // per-tile records: packed row entries + unique columns + 16-bit local columns
-    int ntiles = 0, tile_blks = 0, tile_rows = 0, tile_xcap = 0, grid_tma = 0, spmv_stages = 0, spmv_warps = 0, spmv_xd = 2, spmv_sleep = 100;
+    int ntiles = 0, tile_blks = 0, tile_rows = 0, tile_xcap = 0, grid_tma = 0, spmv_stages = 0, spmv_warps = 0, spmv_xd = 2, spmv_sleep = 100, spmv_ver = 2;
     int64_t spmv_meta_bytes = 0;   // bytes of tile records + headers streamed per SpMV
     bool use_tma = false;
 
