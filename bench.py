@@ -279,10 +279,11 @@ def main():
         "phases_ms": {k: float(np.mean([p[k] for p in phases])) for k in ("assemble_ms", "solve_ms", "update_ms")},
         "ms_per_cg_iteration": float(np.mean([p["solve_ms"] / max(p["cg_iters"], 1) for p in phases])),
         "iteration_gbs_rank0": b_it / (t_dev / args.steps) / 1e9,
+        "iteration_frac_of_peak": b_it / (t_dev / args.steps) / 1e9 / peak,
         "wall_s_timed_region": wall_s,
         "gpu_launches": int(gpu_launches),
         "clocks": sampler.summary(),
-        "roofline": {"bound": "hbm", "kernel": "k_spmv_stream<3,true> (TMA-streamed block-CSR SpMV + p.Ap dot), rank 0",
+        "roofline": {"bound": "hbm", "kernel": "k_spmv_stream2<3,true> (TMA-streamed, warp-specialised block-CSR SpMV + p.Ap dot), rank 0",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
                      "traffic": traffic, "bytes_per_launch": spmv_bytes, "avg_launch_ms": avg_spmv_ms,
                      "launches_timed": int(spmv_n),
