@@ -1,8 +1,8 @@
 #!/usr/bin/env python
 """bench.py — elements/s per Newton iteration (assembly + PCG + state update) of the mechanical hot path.
 
-Workload (BASELINE.json configs[2], the configuration the metric's target is quoted on): HEX20 block, n^3 elements per
-GPU (n=100 -> 1 M elements, 12.27 M dofs per GPU), von Mises E=210e6 nu=0.3 fy=240e3 H=0, bottom clamped, rigid footing
+Workload (BASELINE.json configs[2], the configuration the metric's target is quoted on): HEX20 block of n^3 elements
+(n=100 -> 1 M elements, 12.27 M dofs), von Mises E=210e6 nu=0.3 fy=240e3 H=0, bottom clamped, rigid footing
 = prescribed uz on a 0.2 x 0.2 patch in the middle of the top face, ten equal load increments.  A "step"
 is ONE Newton iteration of the first increment: mount_K on the plastic trial state -> solve_system! (PCG to cg_rtol) ->
 state restore -> update_state!.  Every timed step does identical work (each restarts from the converged state,
@@ -14,9 +14,11 @@ mech-solver.jl:333).
   cpu_baseline: the CPU oracle (restated reference path: COO assembly -> sparse -> direct LU -> state update) on a
             bounded sample (rank 0, N=1 only)
 
-`--impl reference` times that CPU path alone.  Multi-GPU (torchrun, one rank per GPU): weak scaling — the block grows to
-(Nx*n, Ny*n, Nz*n) elements with Nx*Ny*Nz = N as cubic as possible, partitioned by recursive coordinate bisection with
-duplicated halo elements; the PCG exchanges halo entries of p and two small all-reduces per iteration over NCCL.
+`--impl reference` times that CPU path alone.  Multi-GPU (torchrun, one rank per GPU): STRONG scaling by default — the same
+1 M-element configs[2] problem is partitioned over the N GPUs by recursive coordinate bisection with duplicated halo
+elements (the CG iteration count is then the same for every N, so the driver's efficiency measures kernels + exchange and
+not the growth of the Jacobi-PCG iteration count with the domain, profiles/README.md); the PCG exchanges halo entries of p
+and two small all-reduces per iteration over NCCL.  `--scaling weak` grows the block to (Nx*n, Ny*n, Nz*n) elements instead.
 """
 from __future__ import annotations
 
@@ -118,7 +120,7 @@ def run_reference(args, rank, world):
     sample = (f"HEX20 {n}^3 = {info['nelems']} elements / {info['ndofs']} dofs von Mises footing, one Newton iteration per "
               f"step (COO mount_K + scipy SuperLU direct solve standing in for UMFPACK + update_state!), CPU oracle port")
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * t, "higher_is_better": True, "scaling": "weak",
+            "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * t, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "configs[2]: HEX20 von Mises footing (bounded sample)", "sample_n": n},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
@@ -132,7 +134,8 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--size", type=int, default=100, help="HEX20 elements per side PER GPU (100 -> 1 M elements per GPU)")
+    ap.add_argument("--size", type=int, default=100, help="HEX20 elements per side (100 -> 1 M elements; per GPU under --scaling weak)")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
     ap.add_argument("--cpu-size", type=int, default=12, help="elements per side of the CPU baseline sample")
     ap.add_argument("--cg-rtol", type=float, default=1e-10)
     ap.add_argument("--cg-maxit", type=int, default=200000)
@@ -160,7 +163,7 @@ def main():
 
     pc = L.PRECOND[args.precond]
     n = args.size
-    mult = GRID.get(world, (world, 1, 1))
+    mult = GRID.get(world, (world, 1, 1)) if args.scaling == "weak" else (1, 1, 1)
     t_setup = time.perf_counter()
     model, bcs = footing_model(n, mult)
     eqid, nu, setup = model.configure_dofs(bcs)
@@ -268,9 +271,9 @@ def main():
     b_it = b_asm + b_upd + float(np.mean(cg_iters)) * b_cg + 2 * nip * 8 * S
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-        "ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"configs[2]: HEX20 von Mises footing, {n}^3 elements per GPU, block {mult[0]}x{mult[1]}x{mult[2]}, "
+        "config": {"workload": f"configs[2]: HEX20 von Mises footing, {n * mult[0]}x{n * mult[1]}x{n * mult[2]} elements over {world} GPU(s), "
                                "one Newton iteration per step", "elements": nelem_total, "dofs": ndofs, "nnz_rank0": int(dm.nnz),
                    "cg_rtol": args.cg_rtol, "precond": args.precond, "cg_iters_per_step": cg_iters,
                    "l2": "inputs (K = %.1f GB per GPU) larger than L2" % (dm.nnz * 8 / 1e9),
