@@ -125,7 +125,8 @@ amaru_model *create_impl(const CreateArgs &a) {
     int64_t eoff = 0, coff = 0, ipoff = 0;
     m->batches.resize(a.nbatches);
     for (int b = 0; b < a.nbatches; b++) {
-        AMARU_REQUIRE(amaru_shape_info(a.batch_shape[b], info[b]), AMARU_ERR_UNSUPPORTED,
+        AMARU_REQUIRE(a.batch_shape[b] >= AMARU_SHAPE_QUAD4 && a.batch_shape[b] <= AMARU_SHAPE_TET10 &&
+                          amaru_shape_info(a.batch_shape[b], info[b]), AMARU_ERR_UNSUPPORTED,
                       "amaru_create: cell shape outside the hot path (QUAD4, QUAD8, HEX8, HEX20, TET10)");
         AMARU_REQUIRE(info[b].nd == a.ndim, AMARU_ERR_ARG, "amaru_create: cell shape dimension differs from ndim");
         Batch &B = m->batches[b];

@@ -45,6 +45,9 @@ static const double NAT_HEX8[] = {-1, -1, -1, 1, -1, -1, 1, 1, -1, -1, 1, -1, -1
 static const double NAT_HEX20[] = {-1, -1, -1, 1, -1, -1, 1, 1, -1, -1, 1, -1, -1, -1, 1, 1, -1, 1, 1, 1, 1, -1, 1, 1,
                                    0, -1, -1, 1, 0, -1, 0, 1, -1, -1, 0, -1, 0, -1, 1, 1, 0, 1, 0, 1, 1, -1, 0, 1,
                                    -1, -1, 0, 1, -1, 0, 1, 1, 0, -1, 1, 0};
+static const double NAT_LIN2[] = {-1, 1};
+static const double NAT_LIN3[] = {-1, 1, 0};
+static const double NAT_TRI6[] = {0, 0, 1, 0, 0, 1, .5, 0, .5, .5, 0, .5};
 static const double NAT_TET10[] = {0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0, 1, .5, 0, 0, .5, .5, 0, 0, .5, 0, 0, 0, .5, .5, 0, .5, 0, .5, .5};
 
 static void eval_box(int nn, int nd, const double *nat, const double *R, double *N, double *D) {
@@ -136,6 +139,10 @@ bool amaru_shape_info(int id, ShapeInfo &s) {
     case AMARU_SHAPE_HEX8: s.nn = 8; s.nd = 3; nat = NAT_HEX8; break;
     case AMARU_SHAPE_HEX20: s.nn = 20; s.nd = 3; nat = NAT_HEX20; break;
     case AMARU_SHAPE_TET10: s.nn = 10; s.nd = 3; nat = NAT_TET10; break;
+    // facet shapes (src/shape/lines.jl:10-108, src/shape/solids2d.jl:99-151): only used by the load integration
+    case AMARU_SHAPE_LIN2: s.nn = 2; s.nd = 1; nat = NAT_LIN2; break;
+    case AMARU_SHAPE_LIN3: s.nn = 3; s.nd = 1; nat = NAT_LIN3; break;
+    case AMARU_SHAPE_TRI6: s.nn = 6; s.nd = 2; nat = NAT_TRI6; break;
     default: return false;
     }
     s.nat.assign(nat, nat + s.nn * s.nd);
@@ -144,6 +151,13 @@ bool amaru_shape_info(int id, ShapeInfo &s) {
         const double a = 0.5854101966249685, b = 0.1381966011250105, w = 0.04166666666666667;  // quadrature.jl:110-114
         const double t[16] = {a, b, b, w, b, a, b, w, b, b, a, w, b, b, b, w};
         s.ips.assign(t, t + 16);
+    } else if (id == AMARU_SHAPE_TRI6) {
+        const double t[12] = {1.0 / 6, 1.0 / 6, 0, 1.0 / 6, 2.0 / 3, 1.0 / 6, 0, 1.0 / 6, 1.0 / 6, 2.0 / 3, 0, 1.0 / 6};  // quadrature.jl:37-40
+        s.ips.assign(t, t + 12);
+    } else if (s.nd == 1) {
+        const double gl = 0.577350269189625764509149;  // quadrature.jl:16-18 (LIN_IP2)
+        const double t[8] = {-gl, 0, 0, 1.0, gl, 0, 0, 1.0};
+        s.ips.assign(t, t + 8);
     } else if (s.nd == 2) {
         for (int j = -1; j <= 1; j += 2)
             for (int i = -1; i <= 1; i += 2) {
@@ -162,7 +176,7 @@ bool amaru_shape_info(int id, ShapeInfo &s) {
     s.N.resize((size_t)s.nip * s.nn);
     s.dNdR.resize((size_t)s.nip * s.nn * s.nd);
     for (int q = 0; q < s.nip; q++) {
-        if (id == AMARU_SHAPE_TET10)
+        if (id == AMARU_SHAPE_TET10 || id == AMARU_SHAPE_TRI6)
             eval_simplex2(s.nn, s.nd, nat, &s.ips[4 * q], &s.N[(size_t)q * s.nn], &s.dNdR[(size_t)q * s.nn * s.nd]);
         else
             eval_box(s.nn, s.nd, nat, &s.ips[4 * q], &s.N[(size_t)q * s.nn], &s.dNdR[(size_t)q * s.nn * s.nd]);

@@ -69,7 +69,7 @@ def _dyn_stage_solver(ana, stage, tol, dTmin, dTmax, maxits, autoinc, alpha, bet
             model.V[...] = 0.0
             model.A[...] = 0.0
             dm.assemble_K()
-            Uex, Fex = model.get_bc_vals(eqid, setup, 0.0)
+            Uex, Fex = model.get_bc_vals(eqid, setup, 0.0, device=dm)
             dm.set_system_matrix(0.0, 1.0)
             Fex0 = np.ascontiguousarray(Fex.copy())
             dm.solve(A, Fex0, cg_rtol, cg_maxit, pc)                   # solve_system!(M, A, Fex, nu)
@@ -105,7 +105,7 @@ def _dyn_stage_solver(ana, stage, tol, dTmin, dTmax, maxits, autoinc, alpha, bet
             dt = tspan * dT
             inc += 1
             log.append(f"  inc {inc}")
-            Uex, Fex = model.get_bc_vals(eqid, setup, t + dt)
+            Uex, Fex = model.get_bc_vals(eqid, setup, t + dt, device=dm)   # loads re-integrated on the device every step (:346)
             Fex_Fin = Fex - Fina
             dUa[:] = 0.0
             dUi[:] = Uex

@@ -58,6 +58,11 @@ SYMBOLS = {
     "amaru_assemble_M": (C.c_int, [_vp, _dp, C.c_char_p, C.c_int]),
     "amaru_set_system_matrix": (C.c_int, [_vp, C.c_double, C.c_double, C.c_char_p, C.c_int]),
     "amaru_matvec": (C.c_int, [_vp, C.c_double, C.c_double, _dp, _dp, C.c_char_p, C.c_int]),
+    "amaru_loadset_create": (C.c_int, [_vp, C.c_int, C.c_int64, _i32p, C.POINTER(_vp), C.c_char_p, C.c_int]),
+    "amaru_loadset_nip": (C.c_int64, [_vp]),
+    "amaru_loadset_ip_coords": (C.c_int, [_vp, _dp, C.c_char_p, C.c_int]),
+    "amaru_loadset_apply": (C.c_int, [_vp, C.c_int, C.c_double, _dp, _dp, C.c_char_p, C.c_int]),
+    "amaru_loadset_destroy": (C.c_int, [_vp]),
     "amaru_newton_iteration_device": (C.c_int, [_vp, C.c_double, C.c_int, C.c_int, _dp, C.POINTER(C.c_int), _dp,
                                                 C.c_char_p, C.c_int]),
     "amaru_set_device_vectors": (C.c_int, [_vp, _dp, _dp, C.c_char_p, C.c_int]),
@@ -166,6 +171,9 @@ class DeviceModel:
 
     def close(self):
         if getattr(self, "h", None):
+            for ls, _ in list(self.__dict__.get("_loadsets", {}).values()):   # load sets hold a pointer to the model
+                ls.close()
+            self.__dict__.pop("_loadsets", None)
             self.lib.amaru_destroy(self.h)
             self.h = None
 
@@ -259,6 +267,10 @@ class DeviceModel:
         self._check(self.lib.amaru_matvec(self.h, float(a), float(b), _d(x), _d(y), self._msg, len(self._msg)))
         return y
 
+    # -- next tier: natural boundary conditions integrated on the device
+    def loadset(self, shape_id, nodes):
+        return LoadSet(self, shape_id, nodes)
+
     # -- measurement hooks
     def set_device_vectors(self, U, F):
         U = np.ascontiguousarray(U, dtype=np.float64)
@@ -286,3 +298,52 @@ class DeviceModel:
         t, n = C.c_double(0), C.c_int64(0)
         self.lib.amaru_get_profile(self.h, C.byref(t), C.byref(n))
         return t.value, n.value
+
+
+LOAD_KEYS = {"tx": 0, "ty": 1, "tz": 2, "tn": 3, "wx": 0, "wy": 1, "wz": 2}
+
+
+class LoadSet:
+    """The entities (facets or cells) one SurfaceBC / BodyC selected, resident on the device (``amaru_loadset_*``)."""
+
+    def __init__(self, dm: DeviceModel, shape_id: int, nodes: np.ndarray):
+        self.dm = dm
+        nodes = np.ascontiguousarray(nodes, dtype=np.int32)
+        self.nents = nodes.shape[0]
+        h = _vp()
+        st = dm.lib.amaru_loadset_create(dm.h, int(shape_id), self.nents, nodes.ctypes.data_as(_i32p), C.byref(h), dm._msg,
+                                         len(dm._msg))
+        dm._check(st)
+        self.h = h
+        self.nip = dm.lib.amaru_loadset_nip(h)
+
+    def ip_coords(self):
+        X = np.empty((self.nip, 3))
+        self.dm._check(self.dm.lib.amaru_loadset_ip_coords(self.h, _d(X), self.dm._msg, len(self.dm._msg)))
+        return X
+
+    def apply(self, key, vals, F):
+        """F += nodal forces of the set; ``key`` in tx ty tz tn | wx wy wz (or the AMARU_LOAD_* code); ``vals`` a scalar
+        or one value per integration point."""
+        assert F.dtype == np.float64 and F.flags.c_contiguous
+        k = LOAD_KEYS.get(key, key) if isinstance(key, str) else int(key)
+        if isinstance(k, str):
+            k = -1                              # the library answers with the reference's "not applicable" message
+        if np.ndim(vals) == 0:
+            cval, vip = float(vals), None
+        else:
+            cval, vip = 0.0, np.ascontiguousarray(vals, dtype=np.float64)
+            assert vip.size == self.nip
+        self.dm._check(self.dm.lib.amaru_loadset_apply(self.h, k, cval, _d(vip), _d(F), self.dm._msg, len(self.dm._msg)))
+        return F
+
+    def close(self):
+        if getattr(self, "h", None) and getattr(self.dm, "h", None):
+            self.dm.lib.amaru_loadset_destroy(self.h)
+        self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -264,7 +264,10 @@ class FEModel:
         return eq.reshape(self.nnodes, nd).astype(np.int32), nu, setup
 
     # ------------------------------------------------------------------ get_bc_vals (bc.jl:237-249)
-    def get_bc_vals(self, eqid, setup, t=0.0):
+    def get_bc_vals(self, eqid, setup, t=0.0, device=None):
+        """``device``: a lib.DeviceModel of this stage -> the distributed loads (SurfaceBC tx/ty/tz/tn, BodyC wx/wy/wz) are
+        integrated on the GPU (amaru_loadset_*, csrc/loads.cu); the value expressions are evaluated here, on the
+        integration-point coordinates the library returns.  Without it the numpy path below is used (multi-GPU runs)."""
         nd = self.ndim
         ndofs = eqid.size
         U = np.zeros(ndofs)
@@ -288,6 +291,8 @@ class FEModel:
                         n = fn.reshape(-1)
                         U[eqid[n, ESSENTIAL.index(key)]] = np.broadcast_to(
                             evaluate(val, x=X[n, 0], y=X[n, 1], z=X[n, 2], t=t), n.shape)
+                    elif device is not None:
+                        self._device_load(device, ("S", id(bc)), self.shape.facet_shape.id, fn, key, val, t, F)
                     else:
                         Fd = self._boundary_forces(fn, key, val, t)   # (nf, nfn, nd)
                         np.add.at(F, eqid[fn].reshape(-1), Fd.reshape(-1))
@@ -298,10 +303,31 @@ class FEModel:
                         n = self.conn[elems].reshape(-1)
                         U[eqid[n, ESSENTIAL.index(key)]] = np.broadcast_to(
                             evaluate(val, x=X[n, 0], y=X[n, 1], z=X[n, 2], t=t), n.shape)
+                    elif device is not None:
+                        self._device_load(device, ("B", id(bc)), self.shape.id, self.conn[elems], key, val, None, F)
                     else:
                         Fd = self._body_forces(elems, key, val)
                         np.add.at(F, eqid[self.conn[elems]].reshape(-1), Fd.reshape(-1))
         return U, F
+
+    def _device_load(self, dm, ckey, shape_id, nodes, key, val, t, F):
+        """One (bc, key) of bc.jl:116-136 / 175-194 through the device load set of that bc (cached on the handle)."""
+        cache = dm.__dict__.setdefault("_loadsets", {})
+        if ckey not in cache:
+            ls = dm.loadset(shape_id, nodes)
+            cache[ckey] = (ls, None)
+        ls, X = cache[ckey]
+        if isinstance(val, (int, float)):
+            vals = float(val)
+        else:
+            if X is None:
+                X = ls.ip_coords()
+                cache[ckey] = (ls, X)
+            kw = dict(x=X[:, 0], y=X[:, 1], z=X[:, 2])
+            if t is not None:
+                kw["t"] = t
+            vals = np.ascontiguousarray(np.broadcast_to(evaluate(val, **kw), (X.shape[0],)), dtype=np.float64)
+        ls.apply(key, vals, F)
 
     # mech_boundary_forces (src/mech/elem/distributed.jl:76-152), vectorised over facets
     def _boundary_forces(self, fn, key, val, t):

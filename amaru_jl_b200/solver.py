@@ -92,7 +92,7 @@ def _mech_stage_solver(ana, stage, tol, rtol, dT0, dTmin, dTmax, rspan, maxits, 
         dUa = np.zeros(ndofs)
         dUi = np.zeros(ndofs)
         Rc = np.zeros(ndofs)
-        Uex, Fex = model.get_bc_vals(eqid, setup)                     # :269
+        Uex, Fex = model.get_bc_vals(eqid, setup, device=dm)          # :269
         solstatus = success()
         eqflat = eqid.reshape(-1)
 

@@ -48,6 +48,10 @@ extern "C" {
 #define AMARU_SHAPE_HEX8 3   /* nn 8,  nd 3, HEX_IP8  */
 #define AMARU_SHAPE_HEX20 4  /* nn 20, nd 3, HEX_IP8  */
 #define AMARU_SHAPE_TET10 5  /* nn 10, nd 3, TET_IP4  */
+/* facet shapes, accepted by amaru_loadset_create only (src/shape/lines.jl, solids2d.jl:99-151) */
+#define AMARU_SHAPE_LIN2 101 /* nn 2, LIN_IP2 : edge of QUAD4 */
+#define AMARU_SHAPE_LIN3 102 /* nn 3, LIN_IP2 : edge of QUAD8 */
+#define AMARU_SHAPE_TRI6 103 /* nn 6, TRI_IP3 : face of TET10 */
 
 /* material kinds; params[8] = {E, nu, p2, p3, p4, rho, 0, 0} */
 #define AMARU_MAT_LINEAR_ELASTIC 1 /* linear-elastic.jl:12-20 : E, nu                                    */
@@ -165,6 +169,31 @@ int amaru_assemble_M(amaru_model *m, const double *rho, char *msg, int msglen);
 int amaru_set_system_matrix(amaru_model *m, double a, double b, char *msg, int msglen);
 /* y = (a*K + b*M) x over all ndofs (eq_id ordering), e.g. M*A, C*V products of dyn-solver.jl:378,399 */
 int amaru_matvec(amaru_model *m, double a, double b, const double *x, double *y, char *msg, int msglen);
+
+/* ---- next tier: natural boundary conditions integrated on the device ---------------------------
+ * SurfaceBC / BodyC of the reference (src/bc.jl:116-136,175-194) call, per facet / element and per key,
+ * mech_boundary_forces / mech_solid_body_forces (src/mech/elem/distributed.jl:76-152,157-217) and add the result
+ * into F through the facet's dof map.  A load set is the list of entities one boundary condition selected:
+ *   shape   facet shape (LIN2/LIN3 edges of 2D cells; QUAD4/QUAD8/TRI6 faces of 3D cells) => traction keys tx ty tz tn,
+ *           or the cell shape itself (shape dimension == ndim)                             => body-force keys wx wy wz
+ *   nodes   [nents * nn(shape)] node ids, entity-major, in the facet's / element's local node order
+ * Integration uses the DEFAULT quadrature of the shape (get_ip_coords(shape), src/shape/shape.jl:61-64).
+ * The value expression of the condition (a Julia Expr of t,x,y,z) stays on the host: amaru_loadset_ip_coords returns
+ * the integration-point coordinates X = C'N once, the glue evaluates the expression there and passes one value per
+ * integration point (`vip`, entity-major then quadrature order), or NULL + `cval` for a constant. */
+typedef struct amaru_loadset amaru_loadset; /* opaque */
+#define AMARU_LOAD_X 0      /* tx | wx */
+#define AMARU_LOAD_Y 1      /* ty | wy */
+#define AMARU_LOAD_Z 2      /* tz | wz */
+#define AMARU_LOAD_NORMAL 3 /* tn : vip * normalize(n), n = [J2,-J1] (2D) or J[:,1] x J[:,2] (3D), distributed.jl:134-141 */
+int amaru_loadset_create(amaru_model *m, int shape, int64_t nents, const int32_t *nodes, amaru_loadset **out,
+                         char *msg, int msglen);
+int64_t amaru_loadset_nip(const amaru_loadset *ls); /* nents * nip(shape) */
+int amaru_loadset_ip_coords(amaru_loadset *ls, double *X /* [nip*3] */, char *msg, int msglen);
+/* F[ndofs] += sum over entities of the nodal forces (eq_id ordering; same accumulation order as the reference:
+ * entity after entity). */
+int amaru_loadset_apply(amaru_loadset *ls, int key, double cval, const double *vip, double *F, char *msg, int msglen);
+int amaru_loadset_destroy(amaru_loadset *ls);
 
 /* ---- measurement hooks (bench.py): device-resident Newton iteration, no host copies ----------- */
 /* One assemble_K + solve + state_restore + update_state with U/F/dFin kept on the device; returns the
