@@ -241,6 +241,7 @@ void free_model(amaru_model *m) {
     cudaSetDevice(m->device);
     if (m->stream) cudaStreamSynchronize(m->stream);
     amaru_comm_destroy(m);
+    amaru_recovery_destroy(m);
     for (Batch &B : m->batches) {
         cudaFree(B.d_conn); cudaFree(B.d_emat); cudaFree(B.d_map); cudaFree(B.d_perm); cudaFree(B.d_owned);
         cudaFree(B.d_rho); cudaFree(B.d_dNdR); cudaFree(B.d_N); cudaFree(B.d_w);

@@ -134,6 +134,10 @@ struct amaru_model {
     int rank = 0, nranks = 1;
     void *comm = nullptr;          // HaloComm* (halo.cu)
 
+    // output side (recovery.cu)
+    void *recovery = nullptr;      // Recovery*
+    bool recovery_vm_first = true;
+
     // bookkeeping
     int64_t launches = 0;
     bool profiling = false;
@@ -180,3 +184,4 @@ void amaru_allreduce_max_int(amaru_model *m, int *d_val);
 void amaru_comm_setup(amaru_model *m, int nneigh, const int32_t *neigh_rank, const int64_t *send_ptr,
                       const int32_t *send_nodes, const int64_t *recv_start, const int64_t *recv_count, const void *uid);
 void amaru_comm_destroy(amaru_model *m);
+void amaru_recovery_destroy(amaru_model *m);   // recovery.cu

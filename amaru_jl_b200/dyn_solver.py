@@ -16,6 +16,7 @@ Keyword arguments are ``dyn_solver_params`` (dyn-solver.jl:153-172) without the 
 from __future__ import annotations
 
 import math
+import os
 
 import numpy as np
 
@@ -171,6 +172,12 @@ def _dyn_stage_solver(ana, stage, tol, dTmin, dTmax, maxits, autoinc, alpha, bet
                 if checkpoint:
                     Tcheck += dTcheck
                     model.state = dm.get_state()
+                    ana.out += 1                                      # update_records!(checkpoint=true), analysis.jl:83-90
+                    if ana.outdir is not None:
+                        from .output import save, update_output_data
+                        os.makedirs(ana.outdir, exist_ok=True)
+                        update_output_data(model, dm)                 # nodal recovery on the device
+                        save(model, os.path.join(ana.outdir, f"{ana.outkey}-{ana.out}.vtu"))
                 ana.records.append(dict(stage=stage.id, inc=inc, T=T, t=t, U=model.U.copy(), V=model.V.copy(), A=model.A.copy()))
                 if autoinc:
                     if dTbk > 0.0:

@@ -63,6 +63,13 @@ SYMBOLS = {
     "amaru_loadset_ip_coords": (C.c_int, [_vp, _dp, C.c_char_p, C.c_int]),
     "amaru_loadset_apply": (C.c_int, [_vp, C.c_int, C.c_double, _dp, _dp, C.c_char_p, C.c_int]),
     "amaru_loadset_destroy": (C.c_int, [_vp]),
+    "amaru_recovery_create": (C.c_int, [_vp, _u8p, C.c_char_p, C.c_int]),
+    "amaru_recovery_nfields": (C.c_int, [_vp]),
+    "amaru_recovery_field": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_int), C.c_char_p, C.c_int]),
+    "amaru_recover_nodal": (C.c_int, [_vp, _dp, C.c_char_p, C.c_int]),
+    "amaru_write_vtu": (C.c_int, [C.c_char_p, C.c_char_p, C.c_int64, _dp, C.c_int, _i32p, _i64p, _i32p,
+                                  C.c_int, C.POINTER(C.c_char_p), _i32p, _i32p, C.POINTER(_vp),
+                                  C.c_int, C.POINTER(C.c_char_p), _i32p, _i32p, C.POINTER(_vp), C.c_char_p, C.c_int]),
     "amaru_newton_iteration_device": (C.c_int, [_vp, C.c_double, C.c_int, C.c_int, _dp, C.POINTER(C.c_int), _dp,
                                                 C.c_char_p, C.c_int]),
     "amaru_set_device_vectors": (C.c_int, [_vp, _dp, _dp, C.c_char_p, C.c_int]),
@@ -271,6 +278,29 @@ class DeviceModel:
     def loadset(self, shape_id, nodes):
         return LoadSet(self, shape_id, nodes)
 
+    # -- next tier: output side (nodal_patch_recovery on the device)
+    def recovery_create(self, at_bound):
+        ab = np.ascontiguousarray(at_bound, dtype=np.uint8)
+        self._check(self.lib.amaru_recovery_create(self.h, ab.ctypes.data_as(_u8p), self._msg, len(self._msg)))
+
+    def recovery_fields(self):
+        out = []
+        name, code = C.create_string_buffer(32), C.c_int(0)
+        for i in range(self.lib.amaru_recovery_nfields(self.h)):
+            self.lib.amaru_recovery_field(self.h, i, C.byref(code), name, 32)
+            out.append(name.value.decode("utf-8"))
+        return out
+
+    def recover_nodal(self, nnodes):
+        """-> V (nnodes, nfields) like V_rec of nodal_patch_recovery (a transposed view of the field-major buffer)."""
+        nf = self.lib.amaru_recovery_nfields(self.h)
+        if nf < 0:
+            raise AmaruError("recover_nodal: call recovery_create first")
+        V = np.zeros((max(nf, 0), nnodes))
+        if nf > 0:
+            self._check(self.lib.amaru_recover_nodal(self.h, _d(V), self._msg, len(self._msg)))
+        return V.T
+
     # -- measurement hooks
     def set_device_vectors(self, U, F):
         U = np.ascontiguousarray(U, dtype=np.float64)
@@ -347,3 +377,48 @@ class LoadSet:
             self.close()
         except Exception:
             pass
+
+
+_VTU_TYPES = {np.dtype(np.float64): 0, np.dtype(np.int64): 1, np.dtype(np.int32): 2, np.dtype(np.uint64): 3}
+
+
+def write_vtu(filename, coords, batch_shape, batch_nelem, conn, point_data=(), cell_data=(), desc=""):
+    """``amaru_write_vtu``: ASCII .vtu formatted like the reference's save_vtu (src/mesh/io.jl:167-276).
+    ``point_data`` / ``cell_data``: iterables of (name, array) with one row per node / cell."""
+    lib = load()
+    coords = np.ascontiguousarray(coords, dtype=np.float64)
+    bshape = np.ascontiguousarray(batch_shape, dtype=np.int32)
+    bnelem = np.ascontiguousarray(batch_nelem, dtype=np.int64)
+    conn = np.ascontiguousarray(conn, dtype=np.int32).reshape(-1)
+    keep = [coords, bshape, bnelem, conn]
+
+    def pack(items, nrows):
+        items = list(items)
+        n = len(items)
+        names = (C.c_char_p * max(n, 1))()
+        types = np.zeros(max(n, 1), dtype=np.int32)
+        ncomp = np.zeros(max(n, 1), dtype=np.int32)
+        ptrs = (_vp * max(n, 1))()
+        for i, (name, arr) in enumerate(items):
+            arr = np.asarray(arr)
+            if arr.dtype not in _VTU_TYPES:
+                arr = arr.astype(np.float64 if arr.dtype.kind == "f" else np.int64)
+            arr = np.ascontiguousarray(arr)
+            if arr.shape[0] != nrows:
+                raise AmaruError(f"write_vtu: array {name} has {arr.shape[0]} rows, expected {nrows}")
+            keep.append(arr)
+            names[i] = name.encode("utf-8")
+            types[i] = _VTU_TYPES[arr.dtype]
+            ncomp[i] = 1 if arr.ndim == 1 else arr.shape[1]
+            ptrs[i] = arr.ctypes.data
+        keep.extend([types, ncomp])
+        return n, names, types.ctypes.data_as(_i32p), ncomp.ctypes.data_as(_i32p), ptrs
+
+    npt, pn, pt, pc, pp = pack(point_data, coords.shape[0])
+    ncl, cn, ct, cc, cp = pack(cell_data, int(bnelem.sum()))
+    msg = C.create_string_buffer(512)
+    st = lib.amaru_write_vtu(str(filename).encode(), desc.encode("utf-8"), coords.shape[0], _d(coords), len(bshape),
+                             bshape.ctypes.data_as(_i32p), bnelem.ctypes.data_as(_i64p), conn.ctypes.data_as(_i32p),
+                             npt, pn, pt, pc, pp, ncl, cn, ct, cc, cp, msg, 512)
+    if st != OK:
+        raise AmaruStatus(st, msg.value.decode(errors="replace"))

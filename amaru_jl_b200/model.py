@@ -427,7 +427,9 @@ def failure(msg=""):
 class MechAnalysis:
     """MechAnalysis(model) (mech-solver.jl:43-74): sets ctx.thickness, default stress model."""
 
-    def __init__(self, model: FEModel, outdir=".", outkey="out"):
+    def __init__(self, model: FEModel, outdir=None, outkey="out"):
+        """``outdir``: where ``<outkey>-<n>.vtu`` files go at output checkpoints (analysis.jl:76-90).  The reference defaults
+        to "."; here the default None writes nothing (the records stay in ``ana.records``)."""
         self.model = model
         self.ctx = model.ctx
         self.stages: list[Stage] = []
@@ -435,6 +437,7 @@ class MechAnalysis:
         model.ctx.thickness = model.thickness
         if model.ctx.stressmodel == "none":
             model.ctx.stressmodel = "planestrain" if model.ctx.ndim == 2 else "d3"
+        self.out = 0                            # sctx.out: number of output files written
         self.log: list[str] = []
         self.records: list[dict] = []          # one entry per converged increment (what loggers would sample)
         self.stats: list[dict] = []            # per Newton iteration: cg iterations, residue, timings
@@ -443,7 +446,7 @@ class MechAnalysis:
 class DynamicAnalysis(MechAnalysis):
     """DynamicAnalysis(model) (src/mech/dyn-solver.jl:35-66): Newmark time integration; stages carry `tspan`."""
 
-    def __init__(self, model: FEModel, outdir=".", outkey="out"):
+    def __init__(self, model: FEModel, outdir=None, outkey="out"):
         super().__init__(model, outdir, outkey)
         self.t = 0.0
         nd = model.ndim

@@ -190,6 +190,10 @@ TET10 = CellShape("TET10", 5, 3,
                   [[1, 4, 3, 8, 10, 7], [1, 2, 4, 5, 9, 8], [1, 3, 2, 7, 6, 5], [2, 3, 4, 6, 10, 9]],
                   TRI6, _tet_ip4())                                                # solids3d.jl:108-206
 
+# VTK cell types (src/shape/shape.jl:66-96)
+for _s, _v in ((LIN2, 3), (LIN3, 21), (QUAD4, 9), (QUAD8, 23), (TRI6, 22), (HEX8, 12), (HEX20, 25), (TET10, 24)):
+    _s.vtk_type = _v
+
 SHAPES = {s.name: s for s in (LIN2, LIN3, QUAD4, QUAD8, TRI6, HEX8, HEX20, TET10)}
 SOLID_SHAPES_BY_ID = {s.id: s for s in (QUAD4, QUAD8, HEX8, HEX20, TET10)}
 

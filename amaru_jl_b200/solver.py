@@ -16,6 +16,7 @@ Solver keyword arguments are ``mech_solver_params`` (mech-solver.jl:155-168) plu
 from __future__ import annotations
 
 import math
+import os
 import time
 
 import numpy as np
@@ -165,6 +166,12 @@ def _mech_stage_solver(ana, stage, tol, rtol, dT0, dTmin, dTmax, rspan, maxits, 
                 if checkpoint:
                     Tcheck += dTcheck
                     model.state = dm.get_state()                      # what update_records! samples at outputs
+                    ana.out += 1                                      # update_records!(checkpoint=true), analysis.jl:83-90
+                    if ana.outdir is not None:
+                        from .output import save, update_output_data
+                        os.makedirs(ana.outdir, exist_ok=True)
+                        update_output_data(model, dm)                 # nodal recovery on the device
+                        save(model, os.path.join(ana.outdir, f"{ana.outkey}-{ana.out}.vtu"))
                 ana.records.append(dict(stage=stage.id, inc=inc, T=T, U=model.U.copy(), F=model.F.copy()))
                 if autoinc:                                           # :426-455
                     if dTbk > 0.0:

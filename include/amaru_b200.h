@@ -195,6 +195,31 @@ int amaru_loadset_ip_coords(amaru_loadset *ls, double *X /* [nip*3] */, char *ms
 int amaru_loadset_apply(amaru_loadset *ls, int key, double cval, const double *vip, double *F, char *msg, int msglen);
 int amaru_loadset_destroy(amaru_loadset *ls);
 
+/* ---- next tier: output side -------------------------------------------------------------------
+ * nodal_patch_recovery (src/fe-model.jl:506-692): the integration-point fields of ip_state_vals
+ * (src/tools/tensors.jl:162-216; von-mises.jl:159-168; drucker-prager.jl:152-163) are fitted per corner-node patch with
+ * the regression polynomial reg_terms (fe-model.jl:490-503) and averaged at the nodes, on the device, from the IP state
+ * the handle holds.  `at_bound[nnodes]` flags the nodes of model.faces (the outer facets, fe-model.jl:523-529).
+ * Field order is the reference's column order: σxx σyy σzz σyz σxz σxy σvm σ1 [σ2] σ3 εxx εyy εzz [εyz εxz] εxy
+ * (bracketed ones only for the d3 stress model), then `ep` (VonMises) and/or `epa j1 srj2d` (DruckerPrager) in order
+ * of first appearance in the element list.  V is field-major: V[i*nnodes + node] = V_rec[node, i]. */
+int amaru_recovery_create(amaru_model *m, const uint8_t *at_bound, char *msg, int msglen);
+int amaru_recovery_nfields(const amaru_model *m);
+int amaru_recovery_field(const amaru_model *m, int i, int *code, char *name, int namelen);
+int amaru_recover_nodal(amaru_model *m, double *V, char *msg, int msglen);
+
+/* save_vtu (src/mesh/io.jl:167-276, uncompressed branch; XML layout of src/tools/xml.jl:253-316): writes an ASCII
+ * .vtu whose DataArray contents are formatted like the reference's get_array_node! (io.jl:150-163): floats as
+ * "%20.10e" of Float32(value), integers followed by two blanks, one row per line.  Host-side IO, no device work; the
+ * arrays usually come from amaru_recover_nodal and the solution vectors.
+ *   cell data/point data: `n*_arrays` named arrays; type 0 = Float64, 1 = Int64, 2 = Int32, 3 = UInt64; `ncomp` components per row. */
+int amaru_write_vtu(const char *filename, const char *desc, int64_t nnodes, const double *coords, int nbatches,
+                    const int32_t *batch_shape, const int64_t *batch_nelem, const int32_t *conn,
+                    int npoint_arrays, const char *const *point_names, const int32_t *point_type,
+                    const int32_t *point_ncomp, const void *const *point_data,
+                    int ncell_arrays, const char *const *cell_names, const int32_t *cell_type,
+                    const int32_t *cell_ncomp, const void *const *cell_data, char *msg, int msglen);
+
 /* ---- measurement hooks (bench.py): device-resident Newton iteration, no host copies ----------- */
 /* One assemble_K + solve + state_restore + update_state with U/F/dFin kept on the device; returns the
  * CUDA-event time of each phase in ms (4 doubles: assemble, solve, update, total) and CG iterations. */
