@@ -70,6 +70,9 @@ SYMBOLS = {
     "amaru_write_vtu": (C.c_int, [C.c_char_p, C.c_char_p, C.c_int64, _dp, C.c_int, _i32p, _i64p, _i32p,
                                   C.c_int, C.POINTER(C.c_char_p), _i32p, _i32p, C.POINTER(_vp),
                                   C.c_int, C.POINTER(C.c_char_p), _i32p, _i32p, C.POINTER(_vp), C.c_char_p, C.c_int]),
+    "amaru_mesh_block_sizes": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, _i64p, _i64p, C.POINTER(C.c_int)]),
+    "amaru_mesh_block": (C.c_int, [C.c_int, _dp, C.c_int, C.c_int, C.c_int, _dp, _i32p, C.c_char_p, C.c_int]),
+    "amaru_configure_dofs": (C.c_int, [C.c_int64, C.c_int, _u8p, _i32p, _i64p]),
     "amaru_newton_iteration_device": (C.c_int, [_vp, C.c_double, C.c_int, C.c_int, _dp, C.POINTER(C.c_int), _dp,
                                                 C.c_char_p, C.c_int]),
     "amaru_set_device_vectors": (C.c_int, [_vp, _dp, _dp, C.c_char_p, C.c_int]),
@@ -422,3 +425,29 @@ def write_vtu(filename, coords, batch_shape, batch_nelem, conn, point_data=(), c
                              npt, pn, pt, pc, pp, ncl, cn, ct, cc, cp, msg, 512)
     if st != OK:
         raise AmaruStatus(st, msg.value.decode(errors="replace"))
+
+
+def mesh_block(shape_id, c0, c1, nx, ny, nz):
+    """``amaru_mesh_block``: structured box -> (coords (nnodes,3), conn (nelems,nn) int32), reference creation order."""
+    lib = load()
+    nn_, ne_, k_ = C.c_int64(0), C.c_int64(0), C.c_int(0)
+    if lib.amaru_mesh_block_sizes(int(shape_id), int(nx), int(ny), int(nz), C.byref(nn_), C.byref(ne_), C.byref(k_)) != OK:
+        raise AmaruError("block: cannot discretize using this shape / these divisions")
+    coords = np.empty((nn_.value, 3))
+    conn = np.empty((ne_.value, k_.value), dtype=np.int32)
+    box = np.array([c0[0], c0[1], c0[2], c1[0], c1[1], c1[2]], dtype=np.float64)
+    msg = C.create_string_buffer(256)
+    st = lib.amaru_mesh_block(int(shape_id), _d(box), int(nx), int(ny), int(nz), _d(coords), conn.ctypes.data_as(_i32p), msg, 256)
+    if st != OK:
+        raise AmaruStatus(st, msg.value.decode(errors="replace"))
+    return coords, conn
+
+
+def configure_dofs(prescribed):
+    """``amaru_configure_dofs``: (nnodes, nd) bool -> (eqid (nnodes, nd) int32, nu)."""
+    p = np.ascontiguousarray(prescribed, dtype=np.uint8)
+    eq = np.empty(p.shape, dtype=np.int32)
+    nu = C.c_int64(0)
+    if load().amaru_configure_dofs(p.shape[0], p.shape[1], p.ctypes.data_as(_u8p), eq.ctypes.data_as(_i32p), C.byref(nu)) != OK:
+        raise AmaruError("configure_dofs!: bad arguments")
+    return eq, int(nu.value)

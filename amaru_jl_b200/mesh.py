@@ -116,7 +116,9 @@ def _split_block(bl: Block):
 class Mesh:
     """Flat mesh: coords (nnodes,3), conn (nelem,nn) int32, one cell shape, per-element tag index."""
 
-    def __init__(self, *blocks, quiet=True):
+    def __init__(self, *blocks, quiet=True, native=True):
+        """``native``: single blocks are generated by the C++ mesher behind the ABI (``amaru_mesh_block``, csrc/mesher.cpp:
+        same arrays, bit for bit, as the numpy path below, which stays for multi-block meshes and as the cross-check)."""
         bl = []
         for b in blocks:
             bl.extend(b if isinstance(b, (list, tuple)) else [b])
@@ -132,7 +134,12 @@ class Mesh:
         pointdict = {}
         n = 0
         for b in bl:
-            c, onb, conn = _split_block(b)
+            if len(bl) == 1 and native:
+                from . import lib as L
+                c, conn = L.mesh_block(b.cellshape.id, b.c0, b.c1, b.nx, b.ny, b.nz)
+                onb = None
+            else:
+                c, onb, conn = _split_block(b)
             if len(bl) == 1:
                 gid = np.arange(c.shape[0], dtype=np.int64)
                 coords_all.append(c)

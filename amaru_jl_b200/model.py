@@ -256,12 +256,9 @@ class FEModel:
                         presc[np.unique(self.conn[sel]), ESSENTIAL.index(key)] = True
             else:
                 raise AmaruError(f"unsupported boundary condition {type(bc).__name__}")
-        flat = presc.reshape(-1)                                      # node-major, ux,uy,uz per node
-        order = np.concatenate((np.nonzero(~flat)[0], np.nonzero(flat)[0]))   # stable split (bc.jl:220-224)
-        eq = np.empty(flat.size, dtype=np.int64)
-        eq[order] = np.arange(flat.size)
-        nu = int((~flat).sum())
-        return eq.reshape(self.nnodes, nd).astype(np.int32), nu, setup
+        from . import lib as L                                        # node-major, ux,uy,uz per node; stable split
+        eq, nu = L.configure_dofs(presc)                              # (bc.jl:220-224) in C++ behind the ABI
+        return eq, nu, setup
 
     # ------------------------------------------------------------------ get_bc_vals (bc.jl:237-249)
     def get_bc_vals(self, eqid, setup, t=0.0, device=None):

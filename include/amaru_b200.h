@@ -220,6 +220,18 @@ int amaru_write_vtu(const char *filename, const char *desc, int64_t nnodes, cons
                     int ncell_arrays, const char *const *cell_names, const int32_t *cell_type,
                     const int32_t *cell_ncomp, const void *const *cell_data, char *msg, int msglen);
 
+/* ---- next tier: host-side model generation straight into the arrays amaru_create takes ---------
+ * Structured mesher for two-corner box Blocks with uniform spacing (src/mesh/structured.jl:182-231,384-552;
+ * src/mesh/block.jl:3-30): same node creation order (k outer, j, i inner; serendipity points skipped), coordinates
+ * rounded to 8 digits (src/node.jl:57-61), same cell order and local node order (six TET10 per cell,
+ * structured.jl:537-542).  `box` = {x0,y0,z0, x1,y1,z1}; nz ignored for 2D shapes.  Host-only, multi-threaded. */
+int amaru_mesh_block_sizes(int shape, int nx, int ny, int nz, int64_t *nnodes, int64_t *nelems, int *nn);
+int amaru_mesh_block(int shape, const double *box, int nx, int ny, int nz, double *coords /* [nnodes*3] */,
+                     int32_t *conn /* [nelems*nn] */, char *msg, int msglen);
+/* configure_dofs! (src/bc.jl:198-233): `prescribed[nnodes*nd]` flags per (node, ux|uy|uz) -> eq ids with the unknown dofs
+ * first (stable), and nu. */
+int amaru_configure_dofs(int64_t nnodes, int nd, const uint8_t *prescribed, int32_t *eqid, int64_t *nu);
+
 /* ---- measurement hooks (bench.py): device-resident Newton iteration, no host copies ----------- */
 /* One assemble_K + solve + state_restore + update_state with U/F/dFin kept on the device; returns the
  * CUDA-event time of each phase in ms (4 doubles: assemble, solve, update, total) and CG iterations. */
