@@ -80,7 +80,8 @@ def build_patches(nnodes, conn, ncorner, at_bound):
     return patches
 
 
-def nodal_patch_recovery(ndim, planestrain, coords, conn, shape_id, ipcoords, elem_kind, sig, eps, epa, at_bound):
+def nodal_patch_recovery(ndim, planestrain, coords, conn, shape_id, ipcoords, elem_kind, sig, eps, epa, at_bound,
+                         return_deficient=False):
     """-> (V (nnodes, nfields), field names).  ipcoords (nelem*nip, 3), state arrays element-major."""
     nnodes, nelem = coords.shape[0], conn.shape[0]
     nip = ipcoords.shape[0] // nelem
@@ -97,6 +98,7 @@ def nodal_patch_recovery(ndim, planestrain, coords, conn, shape_id, ipcoords, el
     fidx = {k: i for i, k in enumerate(fields)}
     V = np.zeros((nnodes, len(fields)))
     R = np.zeros((nnodes, len(fields)), dtype=np.int64)
+    deficient = np.zeros((nnodes, len(fields)), dtype=bool)      # touched by a rank-deficient sub-patch (pinv = minimum norm)
     for patch in patches:
         if not patch:
             continue
@@ -119,12 +121,17 @@ def nodal_patch_recovery(ndim, planestrain, coords, conn, shape_id, ipcoords, el
                     nt = 6 if m >= 6 else 4 if m >= 4 else 3 if m >= 3 else 1
                 M = np.array([reg_terms(p[0], p[1], p[2], nt, ndim) for p in ips])
                 invM = np.linalg.pinv(M)
+                full_rank = np.linalg.matrix_rank(M) == nt
                 N = np.array([reg_terms(coords[n, 0], coords[n, 1], coords[n, 2], nt, ndim) for n in nodes])
             W = np.array([dict(v)[f] for e in sub for v in vals[e]])
             Vn = N @ (invM @ W)
             V[nodes, fidx[f]] += Vn
             R[nodes, fidx[f]] += 1
+            if not full_rank:
+                deficient[nodes, fidx[f]] = True
     with np.errstate(invalid="ignore", divide="ignore"):
         V = V / R
     V[np.isnan(V)] = 0.0
+    if return_deficient:
+        return V, fields, deficient
     return V, fields

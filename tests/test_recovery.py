@@ -48,10 +48,11 @@ def synthetic_state(model, seed=0, poly=False):
     return np.ascontiguousarray(sig), np.ascontiguousarray(eps), np.ascontiguousarray(epa)
 
 
-def oracle_recover(model, sig, eps, epa):
+def oracle_recover(model, sig, eps, epa, return_deficient=False):
     kinds = np.array([model.materials[i].kind for i in model.elem_mat])
     return OR.nodal_patch_recovery(model.ndim, model.ctx.stressmodel == "planestrain", model.coords, model.conn, model.shape.id,
-                                   model.ip_coords(), kinds, sig, eps, epa, boundary_nodes(model).astype(bool))
+                                   model.ip_coords(), kinds, sig, eps, epa, boundary_nodes(model).astype(bool),
+                                   return_deficient=return_deficient)
 
 
 # ---------------------------------------------------------------------------------------------- CPU: VTU writer
@@ -194,12 +195,19 @@ def test_device_recovery_matches_oracle(shape, n, mats):
     if m.ndim == 2:
         sig[:, [3, 4]] = 0.0
         eps[:, [3, 4]] = 0.0
-    Vo, fo = oracle_recover(m, sig, eps, epa)
+    Vo, fo, deficient = oracle_recover(m, sig, eps, epa, return_deficient=True)
     V, fd = device_recover(m, sig, eps, epa)
     assert fd == fo
+    # Rank-deficient sub-patches exist only in 2D at material interfaces (two stacked elements cannot determine x^2 / y^2):
+    # there the reference's pinv returns a minimum-norm fit that hinges on round-off-level singular values, the device
+    # drops to the next smaller basis.  Everything else must agree.
+    assert not deficient.any() or (m.ndim == 2 and mats == "mixed")
+    assert not deficient[:, :fo.index("εxy") + 1].any()
     for i, name in enumerate(fo):
+        ok = ~deficient[:, i]
         scale = np.abs(Vo[:, i]).max()
-        assert np.abs(V[:, i] - Vo[:, i]).max() <= 1e-9 * max(scale, 1e-30), name
+        assert np.abs(V[ok, i] - Vo[ok, i]).max() <= 1e-9 * max(scale, 1e-30), name
+        assert np.isfinite(V[:, i]).all()
     # principal stresses come out ordered
     i1, i3 = fo.index("σ1"), fo.index("σ3")
     assert (V[:, i1] >= V[:, i3] - 1e-9 * np.abs(V[:, i1]).max()).all()
