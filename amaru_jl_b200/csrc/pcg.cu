@@ -76,6 +76,8 @@ k_cg_init(int64_t nnodes, const double *__restrict__ b, const double *__restrict
         if (threadIdx.x == 0) {
             scal->rz_new = s[0];
             scal->rr = s[1];
+            scal->acc[0] = s[0];   // multi-GPU: all-reduced in place, then k_finalize_scalars
+            scal->acc[1] = s[1];
             if (finalize) {
                 scal->rz_old = s[0];
                 scal->bb = s[1];
@@ -94,7 +96,9 @@ k_cg_update(int64_t nnodes, const double *__restrict__ p, const double *__restri
             const double *__restrict__ Minv, double *x, double *r, double *z, double *partial, CgScalars *scal,
             int finalize) {
     if (scal->done) return;
-    const double alpha = scal->alpha;
+    // single GPU: alpha was finalised by the SpMV's last block; multi-GPU: acc[0] holds the all-reduced p.Ap
+    const double pq_all = scal->acc[0];
+    const double alpha = finalize ? scal->alpha : scal->rz_old / pq_all;
     double s[2] = {0.0, 0.0};
     for (int64_t n = blockIdx.x * (int64_t)ROW_THREADS + threadIdx.x; n < nnodes; n += (int64_t)gridDim.x * ROW_THREADS) {
         double rr[BS], zz[BS];
@@ -119,6 +123,9 @@ k_cg_update(int64_t nnodes, const double *__restrict__ p, const double *__restri
         if (threadIdx.x == 0) {
             scal->rz_new = s[0];
             scal->rr = s[1];
+            if (!finalize) scal->pq = pq_all;   // kept for the breakdown test of k_finalize_scalars (acc is reused below)
+            scal->acc[0] = s[0];
+            scal->acc[1] = s[1];
             if (finalize) {
                 scal->beta = s[0] / scal->rz_old;
                 scal->rz_old = s[0];
@@ -145,13 +152,14 @@ __global__ void k_finalize_scalars(CgScalars *scal, int stage, double tol2, int 
         if (!(scal->acc[0] > 0.0)) scal->done = 3;
         scal->pq = scal->acc[0];
         scal->alpha = scal->rz_old / scal->acc[0];
-    } else {  // after update: acc = {rz_new, rr}
+    } else {  // after update: acc = {rz_new, rr}; a breakdown (p.Ap <= 0 or NaN) shows up as a non-finite r.r here
         if (scal->done) return;
         scal->beta = scal->acc[0] / scal->rz_old;
         scal->rz_old = scal->acc[0];
         scal->rr = scal->acc[1];
         scal->iters += 1;
-        if (scal->acc[1] <= scal->tol2 * scal->bb) scal->done = 1;
+        if (!(scal->pq > 0.0)) scal->done = 3;   // not SPD / breakdown (spmv_dot_epilogue's test on one GPU)
+        else if (scal->acc[1] <= scal->tol2 * scal->bb) scal->done = 1;
         else if (scal->iters >= scal->maxit) scal->done = 2;
         else if (!(scal->acc[1] == scal->acc[1])) scal->done = 3;
     }
@@ -326,11 +334,10 @@ static void cg_loop(amaru_model *m, double rtol, int maxit, SolveInfo &info) {
     k_cg_init<BS, BJ><<<gn, ROW_THREADS, 0, m->stream>>>(m->nowned, m->d_b, m->d_q, m->d_fixed, m->d_Minv, m->d_x, m->d_r,
                                                           m->d_z, m->d_p, m->d_partial, m->d_scal, rtol * rtol, maxit, fin);
     m->launches++;
-    if (multi) {
-        k_stage_scalars<<<1, 1, 0, m->stream>>>(m->d_scal, 2);
+    if (multi) {   // the last block of k_cg_init left the local {r.z, b.b} in acc
         amaru_allreduce_sum(m, m->d_scal->acc, 2);
         k_finalize_scalars<<<1, 1, 0, m->stream>>>(m->d_scal, 0, rtol * rtol, maxit);
-        m->launches += 2;
+        m->launches++;
     }
     const int64_t nloc = m->nowned * BS;
     bool finished = false;
@@ -338,19 +345,16 @@ static void cg_loop(amaru_model *m, double rtol, int maxit, SolveInfo &info) {
         for (int it = 0; it < CG_BATCH; it++) {
             if (multi) amaru_halo_exchange(m, m->d_p);
             spmv_dot(m, m->d_A, m->d_p, m->d_q, fin);
-            if (multi) {
-                k_stage_scalars<<<1, 1, 0, m->stream>>>(m->d_scal, 1);
-                amaru_allreduce_sum(m, m->d_scal->acc, 1);
-                k_finalize_scalars<<<1, 1, 0, m->stream>>>(m->d_scal, 1, 0.0, 0);
-                m->launches += 2;
-            }
+            // multi-GPU: per iteration = halo exchange, SpMV, all-reduce(p.Ap), update, all-reduce(r.z, r.r), one scalar
+            // kernel, p-update; the partial dots are staged by the producing kernels' last blocks and alpha is formed by
+            // the consumer (k_cg_update) from the all-reduced value
+            if (multi) amaru_allreduce_sum(m, m->d_scal->acc, 1);
             k_cg_update<BS, BJ><<<gn, ROW_THREADS, 0, m->stream>>>(m->nowned, m->d_p, m->d_q, m->d_Minv, m->d_x, m->d_r,
                                                                     m->d_z, m->d_partial, m->d_scal, fin);
             if (multi) {
-                k_stage_scalars<<<1, 1, 0, m->stream>>>(m->d_scal, 2);
                 amaru_allreduce_sum(m, m->d_scal->acc, 2);
                 k_finalize_scalars<<<1, 1, 0, m->stream>>>(m->d_scal, 2, 0.0, 0);
-                m->launches += 2;
+                m->launches++;
             }
             k_cg_pupdate<<<node_grid(m, nloc), ROW_THREADS, 0, m->stream>>>(nloc, m->d_z, m->d_p, m->d_scal);
             m->launches += 2;

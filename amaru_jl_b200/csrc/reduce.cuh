@@ -75,6 +75,7 @@ __device__ __forceinline__ void spmv_dot_epilogue(double (&dsum)[1], double *par
         sum_partials<1, NT>(dsum, partial);
         if (threadIdx.x == 0) {
             scal->pq = dsum[0];
+            scal->acc[0] = dsum[0];   // multi-GPU: the local p.Ap is all-reduced in place (no staging kernel)
             if (finalize) {
                 if (!(dsum[0] > 0.0)) scal->done = 3;   // not SPD / breakdown
                 scal->alpha = scal->rz_old / dsum[0];
