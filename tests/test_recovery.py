@@ -198,10 +198,11 @@ def test_device_recovery_matches_oracle(shape, n, mats):
     Vo, fo, deficient = oracle_recover(m, sig, eps, epa, return_deficient=True)
     V, fd = device_recover(m, sig, eps, epa)
     assert fd == fo
-    # Rank-deficient sub-patches exist only in 2D at material interfaces (two stacked elements cannot determine x^2 / y^2):
-    # there the reference's pinv returns a minimum-norm fit that hinges on round-off-level singular values, the device
-    # drops to the next smaller basis.  Everything else must agree.
-    assert not deficient.any() or (m.ndim == 2 and mats == "mixed")
+    # Rank-deficient sub-patches exist only at material interfaces (2D: two stacked elements cannot determine x^2 / y^2;
+    # TET10: two tets of a cell give 8 points that do not span the 7 terms): there the reference's pinv returns a
+    # minimum-norm fit that hinges on round-off-level singular values, the device drops to the next smaller basis
+    # (DESIGN.md).  Everything else must agree.
+    assert not deficient.any() or mats == "mixed"
     assert not deficient[:, :fo.index("εxy") + 1].any()
     for i, name in enumerate(fo):
         ok = ~deficient[:, i]
