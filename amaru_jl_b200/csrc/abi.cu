@@ -252,6 +252,7 @@ void free_model(amaru_model *m) {
                     (void *)m->d_Minv, (void *)m->d_state, (void *)m->d_statebk, (void *)m->d_x, (void *)m->d_r,
                     (void *)m->d_z, (void *)m->d_p, (void *)m->d_q, (void *)m->d_b, (void *)m->d_f, (void *)m->d_io,
                     (void *)m->d_U, (void *)m->d_F, (void *)m->d_U0, (void *)m->d_F0, (void *)m->d_tiles, (void *)m->d_tmeta,
+                    (void *)m->d_stiles, (void *)m->d_stmeta, (void *)m->d_usrc, (void *)m->d_Asym,
                     (void *)m->d_partial, (void *)m->d_scal, (void *)m->d_status})
         cudaFree(p);
     if (m->h_pinned) cudaFreeHost(m->h_pinned);
@@ -374,8 +375,18 @@ int64_t amaru_launch_count(const amaru_model *m) { return m ? m->launches : -1; 
 int64_t amaru_spmv_bytes(const amaru_model *m) {
     if (!m) return -1;
     const int64_t b2 = (int64_t)m->nd * m->nd, n = m->nowned * m->nd;
+    if (m->use_sym)   // CG product from the symmetric storage: upper blocks + records + x once + y zeroed and reduced into once
+        return m->nublk * b2 * 8 + m->sym_meta_bytes + 8 * n + 16 * n;
     const int64_t meta = m->use_tma ? m->spmv_meta_bytes : m->nblk * 4 + (m->nowned + 1) * 4 + n;   // + fixed mask
     return m->nblk * b2 * 8 + meta + 8 * n + 8 * n;
+}
+
+const char *amaru_spmv_kernel(const amaru_model *m) {
+    if (!m) return "";
+    if (m->use_sym) return m->nd == 3 ? "k_spmv_sym<3,true>" : "k_spmv_sym<2,true>";
+    if (m->use_tma) return m->spmv_ver == 2 ? (m->nd == 3 ? "k_spmv_stream2<3,true>" : "k_spmv_stream2<2,true>")
+                                            : (m->nd == 3 ? "k_spmv_stream<3,true>" : "k_spmv_stream<2,true>");
+    return m->nd == 3 ? "k_spmv<3,true>" : "k_spmv<2,true>";
 }
 
 int amaru_set_state(amaru_model *m, const double *sigma, const double *eps, const double *epa, const double *dlam,

@@ -129,6 +129,16 @@ struct amaru_model {
     int ntiles = 0, tile_blks = 0, tile_rows = 0, tile_xcap = 0, grid_tma = 0, spmv_stages = 0, spmv_warps = 0, spmv_xd = 2, spmv_sleep = 100, spmv_ver = 2;
     int64_t spmv_meta_bytes = 0;   // bytes of tile records + headers streamed per SpMV
     bool use_tma = false;
+    // symmetric-storage SpMV of the CG loop (spmv.cu): upper-triangular blocks (col >= row; every owned x ghost block)
+    bool use_sym = false;
+    int64_t nublk = 0;             // stored upper blocks
+    int32_t *d_usrc = nullptr;     // [nublk] index of the block in the full pattern
+    double *d_Asym = nullptr;      // [nublk*nd*nd] values, refreshed whenever d_A changes
+    bool sym_fresh = false;        // d_Asym mirrors the current d_A
+    void *d_stiles = nullptr;      // SpmvTile[nstiles]
+    int32_t *d_stmeta = nullptr;
+    int nstiles = 0, stile_xcap = 0, sgrid = 0, sym_ystages = 2;
+    int64_t sym_meta_bytes = 0;
 
     // multi-GPU
     int rank = 0, nranks = 1;
@@ -166,6 +176,9 @@ void amaru_pcg_setup(amaru_model *m);                                // pcg.cu (
 void amaru_spmv_setup(amaru_model *m);                               // spmv.cu (tiles of the streamed SpMV)
 void amaru_spmv_launch(amaru_model *m, const double *A, const double *x, double *y, int mask, int dot, int check_done,
                        int finalize);                                 // spmv.cu
+// CG-loop product with the symmetric-storage kernel (m->use_sym): y = A x from the upper blocks of the current d_A
+void amaru_spmv_sym_launch(amaru_model *m, const double *x, double *y, int mask, int dot, int check_done, int finalize);
+void amaru_spmv_sym_refresh(amaru_model *m);                          // spmv.cu: d_Asym <- upper blocks of d_A
 void amaru_pcg_solve(amaru_model *m, double rtol, int maxit, int precond, SolveInfo &info);  // pcg.cu
 void amaru_spmv(amaru_model *m, const double *A, const double *x, double *y, int mask_mode);  // pcg.cu
 void amaru_eq_to_nodes(amaru_model *m, const double *d_eq, double *d_nodes);                  // pcg.cu

@@ -298,7 +298,8 @@ static void spmv_dot(amaru_model *m, const double *A, const double *x, double *y
         CUDA_CHECK(cudaEventCreate(&e1));
         CUDA_CHECK(cudaEventRecord(e0, m->stream));
     }
-    amaru_spmv_launch(m, A, x, y, 1, 1, 1, finalize);
+    if (m->use_sym && A == m->d_A) amaru_spmv_sym_launch(m, x, y, 1, 1, 1, finalize);   // half the bytes (spmv.cu)
+    else amaru_spmv_launch(m, A, x, y, 1, 1, 1, finalize);
     if (m->profiling) {
         CUDA_CHECK(cudaEventRecord(e1, m->stream));
         m->ev_pool.push_back(e0);
@@ -394,6 +395,7 @@ void amaru_zero_free(amaru_model *m, double *x) {
 //                              out d_x = full displacement vector, d_q = A*x (reactions at prescribed dofs).
 void amaru_pcg_solve(amaru_model *m, double rtol, int maxit, int precond, SolveInfo &info) {
     build_preconditioner(m, precond);
+    amaru_spmv_sym_refresh(m);   // upper blocks of the current system matrix for the CG products
     const int64_t nloc = m->nowned * m->nd;
     amaru_zero_free(m, m->d_x);   // the first product must be K*[0;U2]
     const bool bj = precond == AMARU_PRECOND_BLOCK_JACOBI;
@@ -460,6 +462,7 @@ void amaru_combine_matrix(amaru_model *m) {
         CUDA_CHECK(cudaGetLastError());
     }
     m->minv_kind = -1;
+    m->sym_fresh = false;
 }
 
 // returns 1 if v[0..n) holds a NaN
@@ -477,6 +480,7 @@ int amaru_check_nan(amaru_model *m, const double *d_v, int64_t n) {
 void amaru_time_cg_kernel(amaru_model *m, int kind, int precond, int reps) {
     const bool bj = precond == AMARU_PRECOND_BLOCK_JACOBI;
     build_preconditioner(m, precond);
+    amaru_spmv_sym_refresh(m);
     CUDA_CHECK(cudaMemsetAsync(m->d_scal, 0, sizeof(CgScalars), m->stream));   // done = 0, alpha = beta = 0
     const int gn = node_grid(m, m->nowned);
     const int64_t nloc = m->nowned * m->nd;

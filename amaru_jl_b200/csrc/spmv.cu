@@ -556,6 +556,292 @@ k_spmv_stream2(int ntiles, const SpmvTile *__restrict__ tiles, const int32_t *__
     if (DOT) spmv_dot_epilogue<STREAM2_THREADS>(dsum, partial, scal, finalize);
 }
 
+
+// ------------------------------------------------------------------------------------------------ symmetric storage
+// K (and a*K + b*M) is symmetric for the three materials of the path (associated flow), so the CG product needs only the
+// blocks with column >= row: HALF the bytes of the dominant kernel.  Stored: for every owned row the blocks (i, j >= i) in
+// local numbering — ghosts are numbered after the owned nodes, so every owned x ghost block is stored too, and the
+// transposed contribution of those (and of the diagonal blocks) is skipped: the neighbour rank owns that row and stores the
+// mirrored block itself.  y_i += A_ij x_j is contracted as in k_spmv_stream2; the transposed part y_j += A_ij' x_i is
+// accumulated per consumer warp in a PRIVATE shared-memory image of the tile's unique columns (no shared atomics: inside a
+// row the block columns are distinct, rows of a warp are separated by __syncwarp), and a seventh warp — the flush warp —
+// sums the four images once all consumers are done with the tile and sends ONE red.global.add.f64 per unique column
+// entry (0.14 reductions per stored value at HEX20) to y, which the host zeroed before the launch.  Prescribed dofs are
+// masked at the flush (3 mask bits ride in the unique-column list).
+//   warps 0..NCW-1 consumers | NCW TMA producer | NCW+1 x-gather | NCW+2 flush
+// The p.Ap dot is accumulated per lane with weight 2 on the blocks whose mirror image is implied and 1 on the others
+// (diagonal, owned x ghost), so it is still one fused, deterministic reduction.  The y accumulation order through the L2
+// reductions varies run to run (last-bit differences in y); AMARU_SPMV_SYM=0 selects the bitwise-reproducible full kernel.
+constexpr int SYM_THREADS = (NCW + 3) * 32;
+constexpr int MAX_YST = 4;
+constexpr uint32_t UCOL_NODE = 0x0fffffffu;   // ucol entry: node | fixed-dof mask << 28 | ghost << 31
+constexpr int LCOL_SKIP = 0x8000;             // lcol entry: (local column)*bs | skip-transposed flag
+
+template <int BS, bool DOT>
+__global__ void __launch_bounds__(SYM_THREADS)
+k_spmv_sym(int ntiles, const SpmvTile *__restrict__ tiles, const int32_t *__restrict__ trec, const double *__restrict__ A,
+           const double *__restrict__ x, double *__restrict__ y, int mask_rows, int tile_blks, int tile_rows, int xcap,
+           int nstages, int rextra, int ystages, int sleep_ns, double *partial, CgScalars *scal, int check_done, int finalize) {
+    if (check_done && scal->done) return;
+    constexpr int B2 = BS * BS;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ uint64_t full_v[MAX_STAGES], empty_v[MAX_STAGES], full_r[MAX_STAGES + XD_MAX], empty_r[MAX_STAGES + XD_MAX],
+        xfull[MAX_STAGES + XD_MAX], ydone[MAX_YST], empty_y[MAX_YST];
+    __shared__ SpmvTile shdr[MAX_STAGES + XD_MAX];
+    const StageLayout L = stage_layout(BS, tile_blks, tile_rows, xcap);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int SV = nstages, SR = nstages + rextra, SY = ystages;
+    unsigned char *vring = smem_raw;
+    unsigned char *rring = smem_raw + (size_t)SV * L.vbytes;
+    const size_t rstride = L.rbytes + L.xbytes;
+    double *yring = reinterpret_cast<double *>(rring + (size_t)SR * rstride);   // [SY][NCW][xcap*BS]
+    const int ylen = (int)(L.xbytes / 8);                                       // doubles per image (>= xcap*BS)
+    if (tid == 0) {
+        for (int s = 0; s < SV; s++) {
+            mbar_init(&full_v[s], 1);
+            mbar_init(&empty_v[s], NCW);
+        }
+        for (int s = 0; s < SR; s++) {
+            mbar_init(&full_r[s], 1);
+            mbar_init(&empty_r[s], NCW + 1);   // consumers + flush warp
+            mbar_init(&xfull[s], 32);
+        }
+        for (int s = 0; s < SY; s++) {
+            mbar_init(&ydone[s], NCW);
+            mbar_init(&empty_y[s], 1);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = tid; i < SY * NCW * ylen; i += SYM_THREADS) yring[i] = 0.0;
+    __syncthreads();
+    const int first = blockIdx.x, stride = gridDim.x;
+    const int nloc = first < ntiles ? (ntiles - first + stride - 1) / stride : 0;
+    double dsum[1] = {0.0};
+
+    if (warp == NCW) {
+        // ============================ TMA producer (as in k_spmv_stream2)
+        uint64_t policy = 0;
+        asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+        SpmvTile hcur{}, hnext{};
+        if (lane < nloc) hcur = tiles[first + lane * stride];
+        if (32 + lane < nloc) hnext = tiles[first + (32 + lane) * stride];
+        int vb0 = 0, vnb = 0;
+        int psr = 0, psv = 0;
+        uint32_t prph = 1u, pvph = 1u;
+        for (int j = 0; j < nloc + rextra; j++) {
+            if (j < nloc) {
+                if ((j & 31) == 0 && j > 0) {
+                    hcur = hnext;
+                    if (j + 32 + lane < nloc) hnext = tiles[first + (j + 32 + lane) * stride];
+                }
+                SpmvTile ti;
+                ti.r0 = __shfl_sync(0xffffffffu, hcur.r0, j & 31);
+                ti.nrows = __shfl_sync(0xffffffffu, hcur.nrows, j & 31);
+                ti.b0 = __shfl_sync(0xffffffffu, hcur.b0, j & 31);
+                ti.nb = __shfl_sync(0xffffffffu, hcur.nb, j & 31);
+                ti.moff = __shfl_sync(0xffffffffu, hcur.moff, j & 31);
+                ti.nu = __shfl_sync(0xffffffffu, hcur.nu, j & 31);
+                ti.recints = __shfl_sync(0xffffffffu, hcur.recints, j & 31);
+                ti.pad = 0;
+                if (lane == (j & 31)) {
+                    vb0 = ti.b0;
+                    vnb = ti.nb;
+                }
+                if (lane == 0) {
+                    const int sr = psr;
+                    if (j >= SR) mbar_wait_backoff(&empty_r[sr], prph, (unsigned)sleep_ns);
+                    shdr[sr] = ti;
+                    const uint64_t rs = ((uint64_t)ti.recints * 4 + 15) & ~15ull;
+                    mbar_arrive_expect_tx(&full_r[sr], (uint32_t)rs);
+                    tma_bulk_g2s(rring + (size_t)sr * rstride, reinterpret_cast<const unsigned char *>(trec + ti.moff),
+                                 (uint32_t)rs, &full_r[sr], policy);
+                }
+                if (++psr == SR) {
+                    psr = 0;
+                    prph ^= 1u;
+                }
+            }
+            const int jv = j - rextra;
+            const int b0 = __shfl_sync(0xffffffffu, vb0, jv & 31), nb = __shfl_sync(0xffffffffu, vnb, jv & 31);
+            if (jv >= 0 && lane == 0) {
+                const int sv = psv;
+                if (jv >= SV) mbar_wait_backoff(&empty_v[sv], pvph, (unsigned)sleep_ns);
+                const uint64_t v0 = (uint64_t)b0 * (B2 * 8), va = v0 & ~15ull;
+                const uint64_t vs = ((v0 + (uint64_t)nb * (B2 * 8) - va) + 15) & ~15ull;
+                mbar_arrive_expect_tx(&full_v[sv], (uint32_t)vs);
+                tma_bulk_g2s(vring + (size_t)sv * L.vbytes, reinterpret_cast<const unsigned char *>(A) + va, (uint32_t)vs,
+                             &full_v[sv], policy);
+            }
+            if (jv >= 0 && ++psv == SV) {
+                psv = 0;
+                pvph ^= 1u;
+            }
+            __syncwarp();
+        }
+    } else if (warp == NCW + 1) {
+        // ============================ gather warp: x entries of the tile's unique columns -> record stage
+        int gs = 0;
+        uint32_t gph = 0;
+        for (int j = 0; j < nloc; j++) {
+            mbar_wait(&full_r[gs], gph);
+            const int nrows_j = shdr[gs].nrows, nu_j = shdr[gs].nu;
+            unsigned char *bj = rring + (size_t)gs * rstride;
+            const uint32_t *ucol = reinterpret_cast<const uint32_t *>(bj) + nrows_j + 1;
+            const uint32_t sxa = smem_u32(bj + L.rbytes);
+            for (int k = lane; k < nu_j; k += 32) {
+                const double *src = x + (int64_t)(ucol[k] & UCOL_NODE) * BS;
+                const uint32_t dst = sxa + (uint32_t)k * (BS * 8u);
+#pragma unroll
+                for (int d = 0; d < BS; d++)
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + d * 8u), "l"(src + d) : "memory");
+            }
+            asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&xfull[gs])) : "memory");
+            if (++gs == SR) {
+                gs = 0;
+                gph ^= 1u;
+            }
+        }
+    } else if (warp == NCW + 2) {
+        // ============================ flush warp: sum the consumers' column images of a finished tile, reduce into y
+        int sr = 0, sy = 0;
+        uint32_t rph = 0, dph = 0;
+        for (int i = 0; i < nloc; i++) {
+            mbar_wait(&full_r[sr], rph);
+            mbar_wait_backoff(&ydone[sy], dph, 40u);
+            const int h_nrows = shdr[sr].nrows, h_nu = shdr[sr].nu;
+            const uint32_t *ucol = reinterpret_cast<const uint32_t *>(rring + (size_t)sr * rstride) + h_nrows + 1;
+            double *img = yring + (size_t)sy * NCW * ylen;
+            for (int u = lane; u < h_nu; u += 32) {
+                const uint32_t uc = ucol[u];
+                double s[BS];
+#pragma unroll
+                for (int c = 0; c < BS; c++) {
+                    double t = 0.0;
+#pragma unroll
+                    for (int w = 0; w < NCW; w++) {
+                        t += img[w * ylen + u * BS + c];
+                        img[w * ylen + u * BS + c] = 0.0;
+                    }
+                    s[c] = t;
+                }
+                if (!(uc >> 31)) {
+                    double *dst = y + (int64_t)(uc & UCOL_NODE) * BS;
+#pragma unroll
+                    for (int c = 0; c < BS; c++)
+                        if (s[c] != 0.0 && !(mask_rows && ((uc >> (28 + c)) & 1u))) atomicAdd(dst + c, s[c]);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(&empty_y[sy]);
+                mbar_arrive(&empty_r[sr]);
+            }
+            if (++sr == SR) {
+                sr = 0;
+                rph ^= 1u;
+            }
+            if (++sy == SY) {
+                sy = 0;
+                dph ^= 1u;
+            }
+        }
+    } else {
+        // ============================ consumer warps
+        constexpr int BPS = 32 / BS;
+        const int b = lane / BS, r = lane - b * BS;
+        const bool act = lane < BPS * BS;
+        const bool writer = lane < BS;
+        int sr = 0, sv = 0, sy = 0;
+        uint32_t rph = 0, vph = 0, yph = 1u;
+        for (int i = 0; i < nloc; i++) {
+            mbar_wait(&full_r[sr], rph);
+            mbar_wait(&xfull[sr], rph);
+            const int h_nrows = shdr[sr].nrows, h_b0 = shdr[sr].b0, h_nu = shdr[sr].nu;
+            const unsigned char *rb = rring + (size_t)sr * rstride;
+            const int32_t *rec = reinterpret_cast<const int32_t *>(rb);
+            const uint16_t *sl = reinterpret_cast<const uint16_t *>(rec + h_nrows + 1 + h_nu);
+            const double *sx = reinterpret_cast<const double *>(rb + L.rbytes);
+            mbar_wait(&full_v[sv], vph);
+            if (i >= SY) mbar_wait(&empty_y[sy], yph);   // the flush warp has emptied (and zeroed) this image
+            double *img = yring + ((size_t)sy * NCW + warp) * ylen;
+            const double *sval = reinterpret_cast<const double *>(vring + (size_t)sv * L.vbytes + (((uint64_t)h_b0 * (B2 * 8)) & 15ull));
+            for (int lr = warp; lr < h_nrows; lr += NCW) {
+                const int32_t e0 = rec[lr], e1 = rec[lr + 1];
+                const int k0 = e0 & 0xffff, nbr = (e1 & 0xffff) - k0;
+                const int dl = ((e0 >> 19) & 0x1fff) * BS;
+                double xi[BS];   // x of the row node: the transposed products need all of it, the dot its component r
+#pragma unroll
+                for (int j = 0; j < BS; j++) xi[j] = sx[dl + j];
+                const double xir = act ? sx[dl + r] : 0.0;
+                double acc = 0.0;
+                if (act) {
+                    for (int k = b; k < nbr; k += BPS) {
+                        const int lc = sl[k0 + k];
+                        const int off = lc & (LCOL_SKIP - 1);
+                        const double *pv = sval + (k0 + k) * B2;
+                        const double *xj = sx + off;
+                        double part = 0.0;
+#pragma unroll
+                        for (int j = 0; j < BS; j++) part += pv[r * BS + j] * xj[j];
+                        acc += part;
+                        if (lc & LCOL_SKIP) {
+                            if (DOT) dsum[0] += xir * part;
+                        } else {
+                            if (DOT) dsum[0] += 2.0 * (xir * part);
+                            double t = 0.0;   // lane (b, c = r): column c of the block times x_i
+#pragma unroll
+                            for (int j = 0; j < BS; j++) t += pv[j * BS + r] * xi[j];
+                            img[off + r] += t;
+                        }
+                    }
+                }
+                double tot = acc;
+                if constexpr (BS == 3) {
+                    const double s1 = tot + __shfl_down_sync(0xffffffffu, tot, 15);
+                    const double u = s1 + __shfl_down_sync(0xffffffffu, s1, 3);
+                    const double v = u + __shfl_down_sync(0xffffffffu, u, 6);
+                    tot = v + __shfl_down_sync(0xffffffffu, s1, 12);
+                } else {
+                    tot += __shfl_xor_sync(0xffffffffu, tot, 2);
+                    tot += __shfl_xor_sync(0xffffffffu, tot, 4);
+                    tot += __shfl_xor_sync(0xffffffffu, tot, 8);
+                    tot += __shfl_xor_sync(0xffffffffu, tot, 16);
+                }
+                if (writer) img[dl + lane] += tot;   // the row node is one of the tile's unique columns (diagonal block)
+                __syncwarp();                        // the next row of this warp may hit the same columns
+            }
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(&empty_v[sv]);
+                mbar_arrive(&empty_r[sr]);
+                mbar_arrive(&ydone[sy]);
+            }
+            if (++sr == SR) {
+                sr = 0;
+                rph ^= 1u;
+            }
+            if (++sv == SV) {
+                sv = 0;
+                vph ^= 1u;
+            }
+            if (++sy == SY) {
+                sy = 0;
+                yph ^= 1u;
+            }
+        }
+    }
+    if (DOT) spmv_dot_epilogue<SYM_THREADS>(dsum, partial, scal, finalize);
+}
+
+__global__ void k_extract_upper(int64_t nublk, int b2, const int32_t *__restrict__ usrc, const double *__restrict__ A,
+                                double *__restrict__ Asym) {
+    const int64_t n = nublk * b2;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t k = i / b2;
+        Asym[i] = A[(int64_t)usrc[k] * b2 + (i - k * b2)];
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ per-lane fallback
 template <int BS, bool DOT>
 __global__ void __launch_bounds__(ROW_THREADS)
@@ -655,6 +941,132 @@ int env_int(const char *name, int dflt) {
     return e ? atoi(e) : dflt;
 }
 
+
+// ---- symmetric-storage tiles: upper pattern (col >= row in local numbering), same record format as the full tiles with
+// ucol = node | fixed mask << 28 | ghost << 31 and lcol = (local column)*bs | skip-transposed << 15
+template <int BS>
+bool configure_sym(amaru_model *m) {
+    const StageLayout L = stage_layout(BS, m->tile_blks, m->tile_rows, m->stile_xcap);
+    const size_t smem = m->spmv_stages * L.vbytes + (size_t)(m->spmv_stages + m->spmv_xd) * (L.rbytes + L.xbytes) +
+                        (size_t)m->sym_ystages * NCW * L.xbytes;
+    if (smem > 220 * 1024) return false;
+    int occ = 0;
+    CUDA_CHECK(cudaFuncSetAttribute(k_spmv_sym<BS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_CHECK(cudaFuncSetAttribute(k_spmv_sym<BS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_spmv_sym<BS, true>, SYM_THREADS, smem));
+    if (occ < 1) return false;
+    m->sgrid = std::min(m->nsm * occ, m->nstiles);
+    return true;
+}
+
+void setup_sym(amaru_model *m) {
+    const int bs = m->nd;
+    m->use_sym = false;
+    if (!m->use_tma || !env_int("AMARU_SPMV_SYM", 1) || m->nnodes >= (1 << 28)) return;
+    m->sym_ystages = std::min(std::max(env_int("AMARU_SPMV_YSTAGES", 2), 1), MAX_YST);
+    const std::vector<int32_t> &rp = m->h_rowptr, &cl = m->h_col;
+    // upper pattern
+    std::vector<int32_t> urp((size_t)m->nowned + 1, 0);
+    for (int64_t r = 0; r < m->nowned; r++) {
+        const int32_t *b = cl.data() + rp[r], *e = cl.data() + rp[r + 1];
+        const int32_t *d = std::lower_bound(b, e, (int32_t)r);
+        if (d == e || *d != (int32_t)r) return;   // a row without diagonal block: keep the full kernel
+        urp[(size_t)r + 1] = urp[(size_t)r] + (int32_t)(e - d);
+    }
+    const int64_t nublk = urp[(size_t)m->nowned];
+    std::vector<int32_t> ucl((size_t)nublk), usrc((size_t)nublk);
+    parallel_chunks(m->nowned, [&](int64_t lo, int64_t hi) {
+        for (int64_t r = lo; r < hi; r++) {
+            const int32_t n = urp[(size_t)r + 1] - urp[(size_t)r], s0 = rp[r + 1] - n;
+            for (int32_t k = 0; k < n; k++) {
+                ucl[(size_t)urp[(size_t)r] + k] = cl[(size_t)s0 + k];
+                usrc[(size_t)urp[(size_t)r] + k] = s0 + k;
+            }
+        }
+    });
+    std::vector<SpmvTile> tiles;
+    for (int64_t r = 0; r < m->nowned;) {
+        const int32_t b0 = urp[r];
+        int64_t e = r;
+        while (e < m->nowned && urp[e + 1] - b0 <= m->tile_blks && e - r < m->tile_rows) e++;
+        if (e == r) return;
+        SpmvTile t{};
+        t.r0 = (int32_t)r; t.nrows = (int32_t)(e - r); t.b0 = b0; t.nb = urp[e] - b0;
+        tiles.push_back(t);
+        r = e;
+    }
+    const int64_t nt = (int64_t)tiles.size();
+    std::vector<int32_t> nu((size_t)nt);
+    parallel_chunks(nt, [&](int64_t lo, int64_t hi) {
+        std::vector<int32_t> tmp;
+        for (int64_t t = lo; t < hi; t++) {
+            tmp.assign(ucl.begin() + tiles[t].b0, ucl.begin() + tiles[t].b0 + tiles[t].nb);
+            std::sort(tmp.begin(), tmp.end());
+            nu[(size_t)t] = (int32_t)(std::unique(tmp.begin(), tmp.end()) - tmp.begin());
+        }
+    });
+    int64_t moff = 0;
+    m->stile_xcap = 1;
+    for (int64_t t = 0; t < nt; t++) {
+        m->stile_xcap = std::max(m->stile_xcap, nu[(size_t)t]);
+        tiles[t].nu = nu[(size_t)t];
+        tiles[t].moff = (int32_t)moff;
+        tiles[t].recints = tiles[t].nrows + 1 + tiles[t].nu + (tiles[t].nb + 1) / 2;
+        moff += (tiles[t].recints + 3) / 4 * 4;
+        if (moff > 2000000000LL) return;
+    }
+    if ((int64_t)m->stile_xcap * bs >= LCOL_SKIP) return;
+    std::vector<int32_t> trec((size_t)moff + 16, 0);
+    const std::vector<uint8_t> &fx = m->h_fixed;
+    parallel_chunks(nt, [&](int64_t lo, int64_t hi) {
+        std::vector<int32_t> tmp;
+        for (int64_t t = lo; t < hi; t++) {
+            const SpmvTile &T = tiles[t];
+            tmp.assign(ucl.begin() + T.b0, ucl.begin() + T.b0 + T.nb);
+            std::sort(tmp.begin(), tmp.end());
+            tmp.erase(std::unique(tmp.begin(), tmp.end()), tmp.end());
+            int32_t *rec = trec.data() + T.moff;
+            for (int32_t lr = 0; lr < T.nrows; lr++) {
+                const int64_t row = T.r0 + lr;
+                const int32_t dl = (int32_t)(std::lower_bound(tmp.begin(), tmp.end(), (int32_t)row) - tmp.begin());
+                rec[lr] = (urp[row] - T.b0) | (dl << 19);   // masks live in the column list here
+            }
+            rec[T.nrows] = T.nb;
+            uint32_t *uc = reinterpret_cast<uint32_t *>(rec + T.nrows + 1);
+            for (size_t k = 0; k < tmp.size(); k++) {
+                const int64_t node = tmp[k];
+                uint32_t v = (uint32_t)node;
+                for (int d = 0; d < bs; d++) v |= (uint32_t)(fx[(size_t)node * bs + d] ? 1u : 0u) << (28 + d);
+                if (node >= m->nowned) v |= 1u << 31;   // ghost: its row belongs to the neighbour rank
+                uc[k] = v;
+            }
+            uint16_t *lc = reinterpret_cast<uint16_t *>(rec + T.nrows + 1 + T.nu);
+            for (int32_t lr = 0; lr < T.nrows; lr++) {
+                const int64_t row = T.r0 + lr;
+                for (int32_t k = urp[row] - T.b0; k < urp[row + 1] - T.b0; k++) {
+                    const int32_t c = ucl[(size_t)T.b0 + k];
+                    const int32_t l = (int32_t)(std::lower_bound(tmp.begin(), tmp.end(), c) - tmp.begin()) * bs;
+                    const bool skip = c == (int32_t)row || c >= m->nowned;   // diagonal block / ghost column
+                    lc[k] = (uint16_t)(l | (skip ? LCOL_SKIP : 0));
+                }
+            }
+        }
+    });
+    m->nstiles = (int)nt;
+    m->nublk = nublk;
+    CUDA_CHECK(cudaMalloc(&m->d_stiles, tiles.size() * sizeof(SpmvTile)));
+    CUDA_CHECK(cudaMemcpy(m->d_stiles, tiles.data(), tiles.size() * sizeof(SpmvTile), cudaMemcpyHostToDevice));
+    CUDA_CHECK(cudaMalloc(&m->d_stmeta, trec.size() * sizeof(int32_t)));
+    CUDA_CHECK(cudaMemcpy(m->d_stmeta, trec.data(), trec.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    CUDA_CHECK(cudaMalloc(&m->d_usrc, std::max<size_t>(usrc.size(), 1) * sizeof(int32_t)));
+    CUDA_CHECK(cudaMemcpy(m->d_usrc, usrc.data(), usrc.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    CUDA_CHECK(cudaMalloc(&m->d_Asym, (size_t)nublk * bs * bs * sizeof(double) + 256));
+    CUDA_CHECK(cudaMemset(m->d_Asym, 0, (size_t)nublk * bs * bs * sizeof(double) + 256));
+    m->sym_meta_bytes = (int64_t)moff * 4 + (int64_t)nt * sizeof(SpmvTile);
+    m->use_sym = (bs == 3) ? configure_sym<3>(m) : configure_sym<2>(m);
+    m->sym_fresh = false;
+}
+
 }  // namespace
 
 // Row tiles + tile-local column compression of the streamed SpMV (host, threaded), uploaded once per pattern.
@@ -744,6 +1156,7 @@ void amaru_spmv_setup(amaru_model *m) {
     CUDA_CHECK(cudaMemcpy(m->d_tmeta, trec.data(), trec.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
     m->spmv_meta_bytes = (int64_t)moff * 4 + (int64_t)nt * sizeof(SpmvTile);
     m->use_tma = (bs == 3) ? configure_stream<3>(m) : configure_stream<2>(m);
+    setup_sym(m);
 }
 
 // y = A x on the owned rows (+ p·Ap partial dot and CG scalar finalisation when dot != 0)
@@ -768,6 +1181,43 @@ void amaru_spmv_launch(amaru_model *m, const double *A, const double *x, double 
             else k_spmv<2, false><<<g, ROW_THREADS, 0, m->stream>>>(m->nowned, m->d_rowptr, m->d_col, A, x, y, m->d_fixed, mask, m->d_partial, m->d_scal, check_done, finalize);
         }
     }
+    m->launches++;
+    CUDA_CHECK(cudaGetLastError());
+}
+
+// d_Asym <- the upper blocks of the current system matrix (called whenever d_A changed, before the next CG loop)
+void amaru_spmv_sym_refresh(amaru_model *m) {
+    if (!m->use_sym || m->sym_fresh) return;
+    const int b2 = m->nd * m->nd;
+    const int64_t n = m->nublk * b2;
+    if (n > 0) {
+        const int g = (int)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, (int64_t)m->nsm * 16));
+        k_extract_upper<<<g, 256, 0, m->stream>>>(m->nublk, b2, m->d_usrc, m->d_A, m->d_Asym);
+        m->launches++;
+        CUDA_CHECK(cudaGetLastError());
+    }
+    m->sym_fresh = true;
+}
+
+// y = A x on the owned rows from the symmetric storage (+ p.Ap); y is zeroed here, the kernel accumulates into it
+void amaru_spmv_sym_launch(amaru_model *m, const double *x, double *y, int mask, int dot, int check_done, int finalize) {
+    CUDA_CHECK(cudaMemsetAsync(y, 0, (size_t)m->nowned * m->nd * sizeof(double), m->stream));
+    const int bs = m->nd;
+    const StageLayout L = stage_layout(bs, m->tile_blks, m->tile_rows, m->stile_xcap);
+    const size_t smem = m->spmv_stages * L.vbytes + (size_t)(m->spmv_stages + m->spmv_xd) * (L.rbytes + L.xbytes) +
+                        (size_t)m->sym_ystages * NCW * L.xbytes;
+#define SYMLAUNCH(BS, DOT)                                                                                                   \
+    k_spmv_sym<BS, DOT><<<m->sgrid, SYM_THREADS, smem, m->stream>>>(                                                           \
+        m->nstiles, reinterpret_cast<const SpmvTile *>(m->d_stiles), m->d_stmeta, m->d_Asym, x, y, mask, m->tile_blks, m->tile_rows, \
+        m->stile_xcap, m->spmv_stages, m->spmv_xd, m->sym_ystages, m->spmv_sleep, m->d_partial, m->d_scal, check_done, finalize)
+    if (bs == 3) {
+        if (dot) SYMLAUNCH(3, true);
+        else SYMLAUNCH(3, false);
+    } else {
+        if (dot) SYMLAUNCH(2, true);
+        else SYMLAUNCH(2, false);
+    }
+#undef SYMLAUNCH
     m->launches++;
     CUDA_CHECK(cudaGetLastError());
 }

@@ -80,6 +80,7 @@ SYMBOLS = {
     "amaru_set_profiling": (C.c_int, [_vp, C.c_int]),
     "amaru_get_profile": (C.c_int, [_vp, _dp, _i64p]),
     "amaru_spmv_bytes": (C.c_int64, [_vp]),
+    "amaru_spmv_kernel": (C.c_char_p, [_vp]),
     "amaru_launch_count": (C.c_int64, [_vp]),
 }
 
@@ -208,6 +209,10 @@ class DeviceModel:
     @property
     def spmv_bytes(self):
         return self.lib.amaru_spmv_bytes(self.h)
+
+    @property
+    def spmv_kernel(self):
+        return self.lib.amaru_spmv_kernel(self.h).decode()
 
     @property
     def launches(self):

@@ -257,7 +257,7 @@ def main():
     traffic = None
     try:   # DRAM bytes per launch of the same kernel on the same matrix from the committed ncu --set full capture
         tj = json.load(open(os.path.join(ROOT, "profiles", "spmv_traffic_r1.json")))
-        if abs(tj["algorithmic_bytes_per_launch"] - spmv_bytes) < 0.02 * spmv_bytes:
+        if tj.get("kernel", "k_spmv_stream2<3,true>").split("(")[0].strip() == dm.spmv_kernel and abs(tj["algorithmic_bytes_per_launch"] - spmv_bytes) < 0.02 * spmv_bytes:
             traffic = tj["dram_bytes_per_launch"]
     except Exception:
         pass
@@ -286,7 +286,7 @@ def main():
         "wall_s_timed_region": wall_s,
         "gpu_launches": int(gpu_launches),
         "clocks": sampler.summary(),
-        "roofline": {"bound": "hbm", "kernel": "k_spmv_stream2<3,true> (TMA-streamed, warp-specialised block-CSR SpMV + p.Ap dot), rank 0",
+        "roofline": {"bound": "hbm", "kernel": f"{dm.spmv_kernel} (TMA-streamed, warp-specialised block-CSR SpMV + p.Ap dot), rank 0",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
                      "traffic": traffic, "bytes_per_launch": spmv_bytes, "avg_launch_ms": avg_spmv_ms,
                      "launches_timed": int(spmv_n),

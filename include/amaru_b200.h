@@ -249,6 +249,8 @@ int amaru_get_profile(amaru_model *m, double *spmv_ms_total, int64_t *spmv_launc
 /* Algorithmic bytes one SpMV launch must move: matrix values + column/row metadata of the storage
  * format actually used + x read once + y written once. */
 int64_t amaru_spmv_bytes(const amaru_model *m);
+/* name of the SpMV kernel the CG loop of this handle launches (for the bench's roofline record) */
+const char *amaru_spmv_kernel(const amaru_model *m);
 /* number of kernels launched by this handle since creation (the bench's gpu_launches claim) */
 int64_t amaru_launch_count(const amaru_model *m);
 

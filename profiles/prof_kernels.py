@@ -29,6 +29,11 @@ dm.assemble_K()
 dU = 0.1 * Uex
 dm.update_state(dU)          # plastic trial state
 dm.assemble_K()
+try:                         # a few CG iterations so that p, q, r hold real data (the timed kernels run on them)
+    dm.solve(dU.copy(), 0.1 * Fex, cg_rtol=1e-30, cg_maxit=5, precond=pc)
+except L.AmaruStatus:
+    pass
+print("spmv kernel:", dm.spmv_kernel, " bytes/launch:", dm.spmv_bytes)
 names = {1: "assemble_K (all colours)", 2: "update (internal forces mode)", 0: "spmv+dot", 3: "cg_update", 4: "cg_pupdate"}
 for kind in (1, 2, 0, 3, 4):
     ms = dm.time_kernel(kind, reps=args.reps, precond=pc)

@@ -388,3 +388,33 @@ def test_full_size_properties_hex20_1M():
     dm.assemble_K()
     assert np.array_equal(dm.matvec(1.0, 0.0, x), Kx) and np.array_equal(v1, Kx)   # bitwise reproducible
     dm.close()
+
+
+@pytest.mark.parametrize("shape,n", [("QUAD8", 6), ("HEX8", 5), ("HEX20", 4), ("TET10", 3)])
+@pytest.mark.parametrize("precond", ["jacobi", "block-jacobi"])
+def test_symmetric_storage_spmv_matches_full_storage(shape, n, precond, monkeypatch):
+    """The CG loop multiplies with the upper blocks only (k_spmv_sym); AMARU_SPMV_SYM=0 selects the full-storage kernel.
+    Same solution within the PCG tolerance, same iteration count within rounding, on the elastic and on a plastic tangent."""
+    model = make_model(shape, n, "vm0" if shape != "QUAD8" else "vm", jitter=0.15, seed=3)
+    bcs = clamp_bcs(model)
+    eqid, nu, setup = model.configure_dofs(bcs)
+    Uex, Fex = model.get_bc_vals(eqid, setup)
+    out = {}
+    for sym in ("1", "0"):
+        monkeypatch.setenv("AMARU_SPMV_SYM", sym)
+        dm = L.DeviceModel(model.flatten(), eqid, eqid.size, nu)
+        try:
+            assert ("sym" in dm.spmv_kernel) == (sym == "1")
+            res = []
+            for it in range(2):
+                dm.assemble_K()
+                U, F = Uex.copy(), Fex.copy()
+                iters, rr = dm.solve(U, F, cg_rtol=1e-12, precond=L.PRECOND[precond])
+                dm.update_state(3.0 * U)                                  # second pass: tangent on a plastic trial state
+                res.append((U, F, iters))
+            out[sym] = res
+        finally:
+            dm.close()
+    for (U1, F1, i1), (U0, F0, i0) in zip(out["1"], out["0"]):
+        assert rel(U1, U0) < 1e-9 and rel(F1[nu:], F0[nu:]) < 1e-9
+        assert abs(i1 - i0) <= max(2, i0 // 50)
