@@ -571,7 +571,9 @@ k_spmv_stream2(int ntiles, const SpmvTile *__restrict__ tiles, const int32_t *__
 //   warps 0..NCW-1 consumers | NCW TMA producer | NCW+1 x-gather | NCW+2 flush
 // The p.Ap dot is accumulated per lane with weight 2 on the blocks whose mirror image is implied and 1 on the others
 // (diagonal, owned x ghost), so it is still one fused, deterministic reduction.  The y accumulation order through the L2
-// reductions varies run to run (last-bit differences in y); AMARU_SPMV_SYM=0 selects the bitwise-reproducible full kernel.
+// reductions varies run to run (last-bit differences in y).  OPT-IN (AMARU_SPMV_SYM=1): on B200 it does not beat the
+// full-storage kernel, see setup_sym; a variant that forms the transposed products with shuffles instead of a second
+// pass over the values in shared memory measured slower still (3.65 ms).
 constexpr int SYM_THREADS = (NCW + 3) * 32;
 constexpr int MAX_YST = 4;
 constexpr uint32_t UCOL_NODE = 0x0fffffffu;   // ucol entry: node | fixed-dof mask << 28 | ghost << 31
@@ -962,7 +964,10 @@ bool configure_sym(amaru_model *m) {
 void setup_sym(amaru_model *m) {
     const int bs = m->nd;
     m->use_sym = false;
-    if (!m->use_tma || !env_int("AMARU_SPMV_SYM", 1) || m->nnodes >= (1 << 28)) return;
+    // Off by default: measured on B200 at 1 M HEX20 elements (profiles/README.md, ncu_spmv_sym_r1.txt) the kernel reads half
+    // the DRAM bytes (9.24 GB vs 18.19 GB) but is bound by the shared-memory / LSU pipe (72 % of peak: the transposed products
+    // re-read the values and read-modify-write the column images) and takes 3.23 ms vs 2.90 ms for the full-storage kernel.
+    if (!m->use_tma || !env_int("AMARU_SPMV_SYM", 0) || m->nnodes >= (1 << 28)) return;
     m->sym_ystages = std::min(std::max(env_int("AMARU_SPMV_YSTAGES", 2), 1), MAX_YST);
     const std::vector<int32_t> &rp = m->h_rowptr, &cl = m->h_col;
     // upper pattern

@@ -393,7 +393,7 @@ def test_full_size_properties_hex20_1M():
 @pytest.mark.parametrize("shape,n", [("QUAD8", 6), ("HEX8", 5), ("HEX20", 4), ("TET10", 3)])
 @pytest.mark.parametrize("precond", ["jacobi", "block-jacobi"])
 def test_symmetric_storage_spmv_matches_full_storage(shape, n, precond, monkeypatch):
-    """The CG loop multiplies with the upper blocks only (k_spmv_sym); AMARU_SPMV_SYM=0 selects the full-storage kernel.
+    """AMARU_SPMV_SYM=1: the CG loop multiplies with the upper blocks only (k_spmv_sym); default is the full-storage kernel.
     Same solution within the PCG tolerance, same iteration count within rounding, on the elastic and on a plastic tangent."""
     model = make_model(shape, n, "vm0" if shape != "QUAD8" else "vm", jitter=0.15, seed=3)
     bcs = clamp_bcs(model)
