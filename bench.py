@@ -158,6 +158,8 @@ def main():
     torch.cuda.set_device(local_rank)
     dist = None
     if world > 1:
+        # NCCL prints its version banner on stdout when the first communicator is made; stdout carries the JSON line only
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
