@@ -150,7 +150,9 @@ def test_config4_tet10_5M_full_size():
         dFin = dm.update_state(Un)
         assert rr <= 1e-10 and iters > 50
         base = np.abs(X[:, 2]) < 1e-9
-        assert abs(Fn[eqid[base, 2]].sum() - 0.01) < 1e-8                      # reactions carry the weight
+        # reactions (K21*U1 + K22*U2, solver.jl:57) balance the load applied on the free dofs; the small share of the body
+        # load lumped on the clamped base nodes themselves never enters the system
+        assert abs(Fn[eqid[base, 2]].sum() + Fex[eqid[~base, 2]].sum()) < 1e-9 and Fn[eqid[base, 2]].sum() > 0.0099
         assert np.abs(dFin[:nu] - Fex[:nu]).max() < 1e-6 * np.abs(Fex).max()   # elastic step: internal = external on free dofs
         assert Un[eqid[:, 2]].min() < 0 and np.isfinite(Un).all()
     finally:
