@@ -182,7 +182,7 @@ __global__ void k_state_permute(int nip, int64_t nelem, int64_t elem_off, int64_
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t es = i / nip;
         const int q = (int)(i - es * nip);
-        const int64_t src_ip = (elem_off + perm[es]) * nip + q;   // ABI position
+        const int64_t src_ip = ip_off + perm[es] * nip + q;       // ABI position: batch after batch (batches may differ in nip)
         const int64_t dev_ip = ip_off + i;
         for (int c = 0; c < ncomp; c++) {
             if (to_device)
