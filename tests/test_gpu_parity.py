@@ -418,3 +418,36 @@ def test_symmetric_storage_spmv_matches_full_storage(shape, n, precond, monkeypa
     for (U1, F1, i1), (U0, F0, i0) in zip(out["1"], out["0"]):
         assert rel(U1, U0) < 1e-9 and rel(F1[nu:], F0[nu:]) < 1e-9
         assert abs(i1 - i0) <= max(2, i0 // 50)
+
+
+def test_edge_cases_single_element_all_prescribed_empty_sets():
+    """Smallest / degenerate inputs: one element; every dof prescribed (nu = 0: solve_system! only forms the reactions
+    K22*U2, solver.jl:32); a boundary condition whose filter selects nothing (empty load set)."""
+    # (HEX8: a single HEX20 with its default 2x2x2 quadrature has spurious zero-energy modes, K11 would be singular)
+    mesh = Mesh(Block([[0, 0, 0], [1, 1, 1]], nx=1, ny=1, nz=1, cellshape="HEX8", tag="solids"))
+    model = FEModel(mesh, [("solids", MechSolid, LinearElastic, dict(E=100.0, nu=0.2))], MechContext())
+    # one element, ordinary solve
+    om, dm, eqid, nu, setup = pair(model, [("z==0", NodeBC(ux=0, uy=0, uz=0)), ("z==1", SurfaceBC(tz=-1.0)),
+                                          ("x>5", SurfaceBC(tx=3.0)), ("x>5", BodyC(wz=1.0))])      # last two select nothing
+    U, F = model.get_bc_vals(eqid, setup, device=dm)
+    assert abs(F.sum() + 1.0) < 1e-12
+    K = check_K(om, dm)
+    Uo, Fo = U.copy(), F.copy()
+    ok, _ = O.solve_system(K.tocsc(), Uo, Fo, nu)
+    dm.solve(U, F, cg_rtol=1e-13)
+    assert ok and rel(U, Uo) < 1e-9 and rel(F[nu:], Fo[nu:]) < 1e-9
+    dm.close()
+    # nu = 0: all dofs prescribed
+    eqid, nu, setup = model.configure_dofs([("x>=0", NodeBC(ux="0.01*x", uy=0, uz="-0.02*z"))])
+    assert nu == 0
+    om = O.OracleModel(model.flatten(), eqid, eqid.size, nu)
+    dm = L.DeviceModel(model.flatten(), eqid, eqid.size, nu)
+    K = check_K(om, dm)
+    U, F = model.get_bc_vals(eqid, setup)
+    Uo, Fo = U.copy(), F.copy()
+    iters, rr = dm.solve(U, F, cg_rtol=1e-12)
+    assert np.array_equal(U, Uo) and rel(F, K @ Uo) < 1e-12
+    dF = dm.update_state(U)
+    dFo, st = om.update_state(Uo)
+    assert st == 0 and rel(dF, dFo) < 1e-12
+    dm.close()
