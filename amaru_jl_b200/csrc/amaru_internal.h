@@ -148,6 +148,8 @@ struct amaru_model {
     void *recovery = nullptr;      // Recovery*
     bool recovery_vm_first = true;
 
+    bool cg_graph = true;          // replay the CG batches as a CUDA graph on one GPU (AMARU_CG_GRAPH=0 disables)
+
     // bookkeeping
     int64_t launches = 0;
     bool profiling = false;

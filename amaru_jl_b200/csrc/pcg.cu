@@ -284,6 +284,8 @@ void amaru_pcg_setup(amaru_model *m) {
     CUDA_CHECK(cudaMalloc(&m->d_scal, sizeof(CgScalars)));
     CUDA_CHECK(cudaMemset(m->d_scal, 0, sizeof(CgScalars)));
     CUDA_CHECK(cudaMallocHost(&m->h_pinned, sizeof(CgScalars) + 64));
+    const char *eg = getenv("AMARU_CG_GRAPH");
+    m->cg_graph = !(eg && atoi(eg) == 0);
 }
 
 // y = A x on the owned rows; mask_mode 1 zeroes the rows of prescribed dofs.  x must hold valid ghost entries.
@@ -341,8 +343,19 @@ static void cg_loop(amaru_model *m, double rtol, int maxit, SolveInfo &info) {
         m->launches++;
     }
     const int64_t nloc = m->nowned * BS;
+    // One batch of CG_BATCH iterations is a fixed sequence of launches with fixed arguments (all scalars live on the device),
+    // so on one GPU it is captured once per solve into a CUDA graph and replayed: small systems (config 1: 1 322 dofs,
+    // 3 launches of a few microseconds per iteration) are launch-bound otherwise.  Not used while the SpMV is being timed
+    // with events, nor on partitioned handles (NCCL calls sit between the kernels).
+    cudaGraphExec_t gexec = nullptr;
+    const bool use_graph = !multi && !m->profiling && m->cg_graph;
     bool finished = false;
     while (!finished) {
+        if (use_graph && gexec) {
+            CUDA_CHECK(cudaGraphLaunch(gexec, m->stream));
+            m->launches += 3 * CG_BATCH;
+        } else {
+        if (use_graph) CUDA_CHECK(cudaStreamBeginCapture(m->stream, cudaStreamCaptureModeThreadLocal));
         for (int it = 0; it < CG_BATCH; it++) {
             if (multi) amaru_halo_exchange(m, m->d_p);
             spmv_dot(m, m->d_A, m->d_p, m->d_q, fin);
@@ -360,11 +373,20 @@ static void cg_loop(amaru_model *m, double rtol, int maxit, SolveInfo &info) {
             k_cg_pupdate<<<node_grid(m, nloc), ROW_THREADS, 0, m->stream>>>(nloc, m->d_z, m->d_p, m->d_scal);
             m->launches += 2;
         }
+        if (use_graph) {
+            cudaGraph_t graph = nullptr;
+            CUDA_CHECK(cudaStreamEndCapture(m->stream, &graph));
+            CUDA_CHECK(cudaGraphInstantiate(&gexec, graph, 0));
+            CUDA_CHECK(cudaGraphDestroy(graph));
+            CUDA_CHECK(cudaGraphLaunch(gexec, m->stream));
+        }
+        }
         CUDA_CHECK(cudaGetLastError());
         CUDA_CHECK(cudaMemcpyAsync(h, m->d_scal, sizeof(CgScalars), cudaMemcpyDeviceToHost, m->stream));
         CUDA_CHECK(cudaStreamSynchronize(m->stream));
         finished = h->done != 0;
     }
+    if (gexec) cudaGraphExecDestroy(gexec);
     info.iters = h->iters;
     info.relres = h->bb > 0.0 ? std::sqrt(h->rr / h->bb) : 0.0;
     info.converged = (h->done == 1);
