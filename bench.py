@@ -157,9 +157,12 @@ def main():
         raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
     dist = None
+    # stdout carries the JSON line only: native libraries (NCCL prints its version banner on stdout when the first
+    # communicator is made) are pointed at stderr for the duration of the run, the line is written to the saved descriptor
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
-        # NCCL prints its version banner on stdout when the first communicator is made; stdout carries the JSON line only
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
@@ -304,7 +307,8 @@ def main():
                                           f"problem, one Newton iteration (COO mount_K + SuperLU direct solve + update_state!) "
                                           f"in {t:.1f} s"}
     if rank == 0:
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     dm.close()
     if dist is not None:
         dist.destroy_process_group()
