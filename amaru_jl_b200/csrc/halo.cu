@@ -67,6 +67,17 @@ struct HaloComm {
     int32_t *d_send_nodes = nullptr;
     double *d_sendbuf = nullptr;
     int64_t nsend = 0;
+    // peer-memory path
+    bool p2p = false;
+    void *d_win = nullptr;                 // this rank's P2PWin
+    void *peer_win[16] = {nullptr};        // every rank's window (own entry = d_win)
+    std::vector<void *> opened;            // cudaIpcOpenMemHandle results to close
+    double **d_peer_p = nullptr;           // [nneigh] neighbours' p vectors
+    int64_t *d_peer_start = nullptr;       // [nneigh] where this rank's nodes start in the neighbour's numbering
+    int64_t *d_send_ptr = nullptr;
+    int *d_neigh = nullptr;
+    unsigned int *d_counter = nullptr;
+    unsigned long long halo_epoch = 0, scal_epoch = 0;
 };
 
 __global__ void k_pack(int64_t n, int nd, const int32_t *__restrict__ nodes, const double *__restrict__ v, double *buf) {
@@ -74,6 +85,86 @@ __global__ void k_pack(int64_t n, int nd, const int32_t *__restrict__ nodes, con
         const int64_t k = i / nd;
         const int d = (int)(i - k * nd);
         buf[i] = v[(int64_t)nodes[k] * nd + d];
+    }
+}
+
+
+// ---- peer-memory path (AMARU_P2P, opt-in): the per-iteration exchanges of the CG loop without NCCL ------------------
+// Every rank exports (cudaIpc) a small window {scalar slots, flags} and its p vector; after amaru_p2p_connect a rank holds
+// device pointers into every peer's window and into its neighbours' p.  Two kernels replace the three NCCL calls of an
+// iteration:
+//   k_p2p_halo       stores the boundary entries of p straight into the neighbours' ghost slots over NVLink, then (last
+//                    block) raises its epoch flag in each neighbour's window and waits for the neighbours' flags;
+//   k_p2p_allreduce  one warp: lane r stores this rank's partial dots into rank r's window (slot of this rank, buffer
+//                    epoch&1) and raises the flag, then the warp waits for all ranks' flags in its own window and sums the
+//                    slots in rank order — every rank forms bitwise the same sum.
+// Safety of the reuse: a slot/flag of parity e&1 is rewritten at epoch e+2, which a rank can only reach after it finished
+// epoch e+1, i.e. after every peer entered epoch e+1, i.e. after every peer finished reading epoch e.  Ghost entries of p
+// are rewritten only after an all-reduce that every rank enters after its SpMV of the previous iteration.
+constexpr int P2P_MAXR = 16;
+struct P2PWin {
+    double slot[2][P2P_MAXR][4];
+    unsigned long long sflag[2][P2P_MAXR];
+    unsigned long long hflag[P2P_MAXR];
+};
+struct P2PDev {
+    int rank, nranks;
+    P2PWin *win[P2P_MAXR];
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__global__ void k_p2p_allreduce(P2PDev pd, unsigned long long epoch, double *vals, int n) {
+    const int lane = threadIdx.x;
+    const int par = (int)(epoch & 1ull);
+    if (lane < pd.nranks) {
+        P2PWin *w = pd.win[lane];
+        for (int k = 0; k < n; k++) w->slot[par][pd.rank][k] = vals[k];
+        __threadfence_system();
+        st_release_sys(&w->sflag[par][pd.rank], epoch);
+    }
+    P2PWin *me = pd.win[pd.rank];
+    if (lane < pd.nranks)
+        while (ld_acquire_sys(&me->sflag[par][lane]) < epoch) __nanosleep(20);
+    __syncwarp();
+    if (lane == 0) {
+        for (int k = 0; k < n; k++) {
+            double s = 0.0;
+            for (int r = 0; r < pd.nranks; r++) s += *reinterpret_cast<volatile double *>(&me->slot[par][r][k]);
+            vals[k] = s;
+        }
+    }
+}
+
+__global__ void k_p2p_halo(P2PDev pd, unsigned long long epoch, int nneigh, const int *__restrict__ neigh,
+                           const int64_t *__restrict__ send_ptr, const int32_t *__restrict__ send_nodes,
+                           double *const *__restrict__ peer_p, const int64_t *__restrict__ peer_start, int nd,
+                           const double *__restrict__ v, unsigned int *counter) {
+    __shared__ bool last;
+    const int64_t total = send_ptr[nneigh] * nd;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t k = i / nd;
+        const int d = (int)(i - k * nd);
+        int q = 0;
+        while (k >= send_ptr[q + 1]) q++;
+        peer_p[q][(peer_start[q] + (k - send_ptr[q])) * nd + d] = v[(int64_t)send_nodes[k] * nd + d];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) last = atomicInc(counter, gridDim.x - 1) == gridDim.x - 1;
+    __syncthreads();
+    if (last && threadIdx.x < nneigh) {
+        __threadfence_system();   // the other blocks' remote stores (fenced before their counter increment) precede the flag
+        st_release_sys(&pd.win[neigh[threadIdx.x]]->hflag[pd.rank], epoch);
+        const unsigned long long *mine = &pd.win[pd.rank]->hflag[neigh[threadIdx.x]];
+        while (ld_acquire_sys(mine) < epoch) __nanosleep(20);
     }
 }
 
@@ -108,6 +199,13 @@ void amaru_comm_destroy(amaru_model *m) {
     HaloComm *hc = static_cast<HaloComm *>(m->comm);
     if (!hc) return;
     if (hc->comm) nccl().CommDestroy(hc->comm);
+    for (void *p : hc->opened) cudaIpcCloseMemHandle(p);
+    cudaFree(hc->d_win);
+    cudaFree(hc->d_peer_p);
+    cudaFree(hc->d_peer_start);
+    cudaFree(hc->d_send_ptr);
+    cudaFree(hc->d_neigh);
+    cudaFree(hc->d_counter);
     cudaFree(hc->d_send_nodes);
     cudaFree(hc->d_sendbuf);
     delete hc;
@@ -119,6 +217,19 @@ void amaru_halo_exchange(amaru_model *m, double *d_v) {
     if (m->nranks <= 1) return;
     HaloComm *hc = static_cast<HaloComm *>(m->comm);
     AMARU_REQUIRE(hc && hc->comm, AMARU_ERR_COMM, "halo exchange: communicator not initialised");
+    if (hc->p2p && d_v == m->d_p) {   // CG loop: push into the neighbours' ghost slots, flag, wait (no NCCL)
+        P2PDev pd;
+        pd.rank = m->rank;
+        pd.nranks = m->nranks;
+        for (int r = 0; r < P2P_MAXR; r++) pd.win[r] = static_cast<P2PWin *>(r < m->nranks ? hc->peer_win[r] : nullptr);
+        const int64_t n = hc->nsend * m->nd;
+        const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, (int64_t)m->nsm * 2));
+        k_p2p_halo<<<blocks, 256, 0, m->stream>>>(pd, ++hc->halo_epoch, hc->nneigh, hc->d_neigh, hc->d_send_ptr, hc->d_send_nodes,
+                                                  hc->d_peer_p, hc->d_peer_start, m->nd, d_v, hc->d_counter);
+        m->launches++;
+        CUDA_CHECK(cudaGetLastError());
+        return;
+    }
     NcclApi &api = nccl();
     if (hc->nsend > 0) {
         const int64_t n = hc->nsend * m->nd;
@@ -139,6 +250,16 @@ void amaru_allreduce_sum(amaru_model *m, double *d_vals, int64_t n) {
     if (m->nranks <= 1) return;
     HaloComm *hc = static_cast<HaloComm *>(m->comm);
     AMARU_REQUIRE(hc && hc->comm, AMARU_ERR_COMM, "all-reduce: communicator not initialised");
+    if (hc->p2p && n <= 4) {   // the scalar all-reduces of the CG loop through peer memory
+        P2PDev pd;
+        pd.rank = m->rank;
+        pd.nranks = m->nranks;
+        for (int r = 0; r < P2P_MAXR; r++) pd.win[r] = static_cast<P2PWin *>(r < m->nranks ? hc->peer_win[r] : nullptr);
+        k_p2p_allreduce<<<1, 32, 0, m->stream>>>(pd, ++hc->scal_epoch, d_vals, (int)n);
+        m->launches++;
+        CUDA_CHECK(cudaGetLastError());
+        return;
+    }
     NCCL_CHECK(nccl().AllReduce(d_vals, d_vals, (size_t)n, ncclDouble, ncclSum, hc->comm, m->stream));
 }
 
@@ -163,6 +284,79 @@ extern "C" int amaru_nccl_unique_id(void *uid128, char *msg, int msglen) {
         ncclUniqueId id;
         NCCL_CHECK(nccl().GetUniqueId(&id));
         std::memcpy(uid128, &id, sizeof(id));
+        return AMARU_OK;
+    } catch (const AmaruError &e) {
+        if (msg && msglen > 0) snprintf(msg, (size_t)msglen, "%s", e.msg.c_str());
+        return e.code;
+    }
+}
+
+// ---- peer-memory path: handle exchange (the host all-gathers the 128-byte records, e.g. with torch.distributed / MPI.jl)
+extern "C" int amaru_p2p_export(amaru_model *m, void *out128, char *msg, int msglen) {
+    try {
+        if (msg && msglen > 0) msg[0] = 0;
+        AMARU_REQUIRE(m && out128, AMARU_ERR_ARG, "amaru_p2p_export: null argument");
+        HaloComm *hc = static_cast<HaloComm *>(m->comm);
+        AMARU_REQUIRE(hc && m->nranks > 1 && m->nranks <= P2P_MAXR, AMARU_ERR_ARG, "amaru_p2p_export: needs a partitioned handle of at most 16 ranks");
+        CUDA_CHECK(cudaSetDevice(m->device));
+        if (!hc->d_win) {
+            CUDA_CHECK(cudaMalloc(&hc->d_win, sizeof(P2PWin)));
+            CUDA_CHECK(cudaMemset(hc->d_win, 0, sizeof(P2PWin)));
+        }
+        cudaIpcMemHandle_t h[2];
+        CUDA_CHECK(cudaIpcGetMemHandle(&h[0], hc->d_win));
+        CUDA_CHECK(cudaIpcGetMemHandle(&h[1], m->d_p));
+        static_assert(sizeof(h) == 128, "two IPC handles");
+        std::memcpy(out128, h, sizeof(h));
+        CUDA_CHECK(cudaDeviceSynchronize());
+        return AMARU_OK;
+    } catch (const AmaruError &e) {
+        if (msg && msglen > 0) snprintf(msg, (size_t)msglen, "%s", e.msg.c_str());
+        return e.code;
+    }
+}
+
+// all_handles: nranks records of 128 bytes in rank order; peer_recv_start[i]: first local node id, in neighbour
+// neigh_rank[i]'s numbering, of the ghost range that neighbour keeps for this rank (its recv_start for this rank)
+extern "C" int amaru_p2p_connect(amaru_model *m, const void *all_handles, const int64_t *peer_recv_start, char *msg, int msglen) {
+    try {
+        if (msg && msglen > 0) msg[0] = 0;
+        AMARU_REQUIRE(m && all_handles, AMARU_ERR_ARG, "amaru_p2p_connect: null argument");
+        HaloComm *hc = static_cast<HaloComm *>(m->comm);
+        AMARU_REQUIRE(hc && hc->d_win && m->nranks > 1 && m->nranks <= P2P_MAXR, AMARU_ERR_ARG, "amaru_p2p_connect: call amaru_p2p_export first");
+        AMARU_REQUIRE(hc->nneigh == 0 || peer_recv_start, AMARU_ERR_ARG, "amaru_p2p_connect: null peer_recv_start");
+        CUDA_CHECK(cudaSetDevice(m->device));
+        const cudaIpcMemHandle_t *H = static_cast<const cudaIpcMemHandle_t *>(all_handles);
+        std::vector<double *> peer_p((size_t)std::max(hc->nneigh, 1), nullptr);
+        for (int r = 0; r < m->nranks; r++) {
+            if (r == m->rank) {
+                hc->peer_win[r] = hc->d_win;
+                continue;
+            }
+            void *w = nullptr;
+            CUDA_CHECK(cudaIpcOpenMemHandle(&w, H[2 * r], cudaIpcMemLazyEnablePeerAccess));
+            hc->opened.push_back(w);
+            hc->peer_win[r] = w;
+        }
+        for (int q = 0; q < hc->nneigh; q++) {
+            void *pp = nullptr;
+            CUDA_CHECK(cudaIpcOpenMemHandle(&pp, H[2 * hc->neigh[q] + 1], cudaIpcMemLazyEnablePeerAccess));
+            hc->opened.push_back(pp);
+            peer_p[(size_t)q] = static_cast<double *>(pp);
+        }
+        const size_t nn = (size_t)std::max(hc->nneigh, 1);
+        CUDA_CHECK(cudaMalloc(&hc->d_peer_p, nn * sizeof(double *)));
+        CUDA_CHECK(cudaMalloc(&hc->d_peer_start, nn * sizeof(int64_t)));
+        CUDA_CHECK(cudaMalloc(&hc->d_send_ptr, (nn + 1) * sizeof(int64_t)));
+        CUDA_CHECK(cudaMalloc(&hc->d_neigh, nn * sizeof(int)));
+        CUDA_CHECK(cudaMalloc(&hc->d_counter, sizeof(unsigned int)));
+        CUDA_CHECK(cudaMemset(hc->d_counter, 0, sizeof(unsigned int)));
+        CUDA_CHECK(cudaMemcpy(hc->d_peer_p, peer_p.data(), hc->nneigh * sizeof(double *), cudaMemcpyHostToDevice));
+        if (hc->nneigh) CUDA_CHECK(cudaMemcpy(hc->d_peer_start, peer_recv_start, hc->nneigh * sizeof(int64_t), cudaMemcpyHostToDevice));
+        CUDA_CHECK(cudaMemcpy(hc->d_send_ptr, hc->send_ptr.data(), (hc->nneigh + 1) * sizeof(int64_t), cudaMemcpyHostToDevice));
+        if (hc->nneigh) CUDA_CHECK(cudaMemcpy(hc->d_neigh, hc->neigh.data(), hc->nneigh * sizeof(int), cudaMemcpyHostToDevice));
+        CUDA_CHECK(cudaDeviceSynchronize());
+        hc->p2p = true;
         return AMARU_OK;
     } catch (const AmaruError &e) {
         if (msg && msglen > 0) snprintf(msg, (size_t)msglen, "%s", e.msg.c_str());

@@ -40,6 +40,8 @@ SYMBOLS = {
                                            C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, _i32p, _i64p, _i32p, _i64p,
                                            _i64p, _vp, C.c_int, C.POINTER(_vp), C.c_char_p, C.c_int]),
     "amaru_nccl_unique_id": (C.c_int, [_vp, C.c_char_p, C.c_int]),
+    "amaru_p2p_export": (C.c_int, [_vp, _vp, C.c_char_p, C.c_int]),
+    "amaru_p2p_connect": (C.c_int, [_vp, _vp, _i64p, C.c_char_p, C.c_int]),
     "amaru_destroy": (C.c_int, [_vp]),
     "amaru_nip_total": (C.c_int64, [_vp]),
     "amaru_nnz": (C.c_int64, [_vp]),
@@ -281,6 +283,23 @@ class DeviceModel:
         y = np.empty(self.ndofs)
         self._check(self.lib.amaru_matvec(self.h, float(a), float(b), _d(x), _d(y), self._msg, len(self._msg)))
         return y
+
+    # -- multi-GPU: peer-memory path of the CG-loop exchanges (one box, NVLink)
+    def p2p_connect(self, all_gather):
+        """``all_gather(obj) -> list of every rank's obj in rank order`` (e.g. torch.distributed.all_gather_object).
+        Exchanges the cudaIpc handles and the ghost offsets, then switches the CG loop's halo exchange and scalar
+        all-reduces from NCCL to the peer-memory kernels (csrc/halo.cu)."""
+        v = self.view
+        buf = C.create_string_buffer(128)
+        self._check(self.lib.amaru_p2p_export(self.h, C.cast(buf, _vp), self._msg, len(self._msg)))
+        mine = dict(handles=bytes(buf.raw), neigh=[int(q) for q in v.neigh], recv_start=[int(s) for s in v.recv_start])
+        everyone = all_gather(mine)
+        allh = b"".join(e["handles"] for e in everyone)
+        peer_start = np.array([everyone[q]["recv_start"][everyone[q]["neigh"].index(int(v.rank))] for q in mine["neigh"]],
+                              dtype=np.int64)
+        hb = C.create_string_buffer(allh, len(allh))
+        self._check(self.lib.amaru_p2p_connect(self.h, C.cast(hb, _vp), peer_start.ctypes.data_as(_i64p), self._msg,
+                                               len(self._msg)))
 
     # -- next tier: natural boundary conditions integrated on the device
     def loadset(self, shape_id, nodes):

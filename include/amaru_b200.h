@@ -116,6 +116,14 @@ int amaru_create_partitioned(int ndim, int stressmodel, double thickness,
                              const int32_t *send_nodes, const int64_t *recv_start, const int64_t *recv_count,
                              const void *nccl_uid, int device, amaru_model **out, char *msg, int msglen);
 int amaru_nccl_unique_id(void *uid128, char *msg, int msglen);
+/* Optional peer-memory path for the per-iteration exchanges of the CG loop (one box, NVLink): every rank exports 128 bytes
+ * (two cudaIpc handles: its flag/scalar window and its p vector), the host all-gathers them in rank order and calls
+ * amaru_p2p_connect with, for every neighbour i of this rank, the first local node id (in THAT neighbour's numbering) of
+ * the ghost range it keeps for this rank (= the neighbour's recv_start entry for this rank).  Afterwards the halo exchange
+ * of p and the scalar all-reduces of the CG loop run as two small kernels over peer memory instead of three NCCL calls;
+ * everything else (result vectors, status flags) stays on NCCL. */
+int amaru_p2p_export(amaru_model *m, void *out128, char *msg, int msglen);
+int amaru_p2p_connect(amaru_model *m, const void *all_handles, const int64_t *peer_recv_start, char *msg, int msglen);
 
 int amaru_destroy(amaru_model *m);
 

@@ -41,6 +41,13 @@ def main():
     uid = [L.nccl_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(uid, src=0)
     dm = L.DeviceModel(lf, eql, ndofs, nu, device=local, view=view, nccl_uid=uid[0])
+    if os.environ.get("AMARU_P2P", "0") == "1":
+
+        def gather(obj):
+            out = [None] * world
+            dist.all_gather_object(out, obj)
+            return out
+        dm.p2p_connect(gather)
     ok = True
     ref = L.DeviceModel(flat, eqid, ndofs, nu, device=local) if rank == 0 else None
     for it in range(2):                                    # second pass: tangent on the plastic trial state
