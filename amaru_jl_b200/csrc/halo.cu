@@ -68,7 +68,7 @@ struct HaloComm {
     double *d_sendbuf = nullptr;
     int64_t nsend = 0;
     // peer-memory path
-    bool p2p = false;
+    bool p2p = false, p2p_ready = false;
     void *d_win = nullptr;                 // this rank's P2PWin
     void *peer_win[16] = {nullptr};        // every rank's window (own entry = d_win)
     std::vector<void *> opened;            // cudaIpcOpenMemHandle results to close
@@ -356,10 +356,20 @@ extern "C" int amaru_p2p_connect(amaru_model *m, const void *all_handles, const 
         CUDA_CHECK(cudaMemcpy(hc->d_send_ptr, hc->send_ptr.data(), (hc->nneigh + 1) * sizeof(int64_t), cudaMemcpyHostToDevice));
         if (hc->nneigh) CUDA_CHECK(cudaMemcpy(hc->d_neigh, hc->neigh.data(), hc->nneigh * sizeof(int), cudaMemcpyHostToDevice));
         CUDA_CHECK(cudaDeviceSynchronize());
-        hc->p2p = true;
+        hc->p2p_ready = true;
         return AMARU_OK;
     } catch (const AmaruError &e) {
         if (msg && msglen > 0) snprintf(msg, (size_t)msglen, "%s", e.msg.c_str());
         return e.code;
     }
+}
+
+// Collective switch: the host calls it with on=1 on EVERY rank only after every rank's amaru_p2p_connect succeeded (a mixed
+// state would leave some ranks waiting on flags while others sit in NCCL calls).
+extern "C" int amaru_p2p_enable(amaru_model *m, int on) {
+    if (!m || !m->comm) return AMARU_ERR_ARG;
+    HaloComm *hc = static_cast<HaloComm *>(m->comm);
+    if (on && !hc->p2p_ready) return AMARU_ERR_ARG;
+    hc->p2p = on != 0;
+    return AMARU_OK;
 }

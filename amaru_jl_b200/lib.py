@@ -42,6 +42,7 @@ SYMBOLS = {
     "amaru_nccl_unique_id": (C.c_int, [_vp, C.c_char_p, C.c_int]),
     "amaru_p2p_export": (C.c_int, [_vp, _vp, C.c_char_p, C.c_int]),
     "amaru_p2p_connect": (C.c_int, [_vp, _vp, _i64p, C.c_char_p, C.c_int]),
+    "amaru_p2p_enable": (C.c_int, [_vp, C.c_int]),
     "amaru_destroy": (C.c_int, [_vp]),
     "amaru_nip_total": (C.c_int64, [_vp]),
     "amaru_nnz": (C.c_int64, [_vp]),
@@ -287,19 +288,27 @@ class DeviceModel:
     # -- multi-GPU: peer-memory path of the CG-loop exchanges (one box, NVLink)
     def p2p_connect(self, all_gather):
         """``all_gather(obj) -> list of every rank's obj in rank order`` (e.g. torch.distributed.all_gather_object).
-        Exchanges the cudaIpc handles and the ghost offsets, then switches the CG loop's halo exchange and scalar
-        all-reduces from NCCL to the peer-memory kernels (csrc/halo.cu)."""
+        Exchanges the cudaIpc handles and the ghost offsets and, if EVERY rank could map its peers, switches the CG loop's
+        halo exchange and scalar all-reduces from NCCL to the peer-memory kernels (csrc/halo.cu).  Returns True when the
+        peer-memory path is on (all ranks agree), False when every rank stays on NCCL."""
         v = self.view
         buf = C.create_string_buffer(128)
-        self._check(self.lib.amaru_p2p_export(self.h, C.cast(buf, _vp), self._msg, len(self._msg)))
-        mine = dict(handles=bytes(buf.raw), neigh=[int(q) for q in v.neigh], recv_start=[int(s) for s in v.recv_start])
+        st = self.lib.amaru_p2p_export(self.h, C.cast(buf, _vp), self._msg, len(self._msg))
+        mine = dict(ok=st == OK, handles=bytes(buf.raw), neigh=[int(q) for q in v.neigh],
+                    recv_start=[int(s) for s in v.recv_start])
         everyone = all_gather(mine)
-        allh = b"".join(e["handles"] for e in everyone)
-        peer_start = np.array([everyone[q]["recv_start"][everyone[q]["neigh"].index(int(v.rank))] for q in mine["neigh"]],
-                              dtype=np.int64)
-        hb = C.create_string_buffer(allh, len(allh))
-        self._check(self.lib.amaru_p2p_connect(self.h, C.cast(hb, _vp), peer_start.ctypes.data_as(_i64p), self._msg,
-                                               len(self._msg)))
+        ok = all(e["ok"] for e in everyone)
+        if ok:
+            allh = b"".join(e["handles"] for e in everyone)
+            peer_start = np.array([everyone[q]["recv_start"][everyone[q]["neigh"].index(int(v.rank))] for q in mine["neigh"]],
+                                  dtype=np.int64)
+            hb = C.create_string_buffer(allh, len(allh))
+            st = self.lib.amaru_p2p_connect(self.h, C.cast(hb, _vp), peer_start.ctypes.data_as(_i64p), self._msg, len(self._msg))
+            ok = st == OK
+        ok = all(all_gather(bool(ok)))
+        if ok:
+            self._check(self.lib.amaru_p2p_enable(self.h, 1))
+        return ok
 
     # -- next tier: natural boundary conditions integrated on the device
     def loadset(self, shape_id, nodes):

@@ -184,13 +184,14 @@ def main():
         uid = [L.nccl_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         dm = L.DeviceModel(lf, eql, ndofs, nu, device=local_rank, view=view, nccl_uid=uid[0])
-        if os.environ.get("AMARU_P2P", "0") == "1":   # CG-loop exchanges through peer memory instead of NCCL
+        p2p_on = False
+        if os.environ.get("AMARU_P2P", "1") == "1":   # CG-loop exchanges through peer memory instead of NCCL (all ranks or none)
 
             def gather(obj):
                 out = [None] * world
                 dist.all_gather_object(out, obj)
                 return out
-            dm.p2p_connect(gather)
+            p2p_on = dm.p2p_connect(gather)
         nlocal_elems, nlocal_nodes = int(view.elem_gid.size), int(view.node_gid.size)
     t_setup = time.perf_counter() - t_setup
     dUex, dFex = 0.1 * Uex, 0.1 * Fex                      # first of ten equal increments
@@ -290,8 +291,8 @@ def main():
                    "cg_rtol": args.cg_rtol, "precond": args.precond, "cg_iters_per_step": cg_iters,
                    "l2": "inputs (K = %.1f GB per GPU) larger than L2" % (dm.nnz * 8 / 1e9),
                    "parallelism": (f"dd{world} (element partition + halo elements, " +
-                                   ("peer-memory halo push + all-reduce kernels)" if os.environ.get("AMARU_P2P", "0") == "1"
-                                    else "NCCL halo exchange)")) if world > 1 else "dd1",
+                                   ("peer-memory halo push + all-reduce kernels)" if p2p_on else "NCCL halo exchange)"))
+                   if world > 1 else "dd1",
                    "setup_s": round(t_setup, 2)},
         "phases_ms": {k: float(np.mean([p[k] for p in phases])) for k in ("assemble_ms", "solve_ms", "update_ms")},
         "ms_per_cg_iteration": float(np.mean([p["solve_ms"] / max(p["cg_iters"], 1) for p in phases])),

@@ -124,6 +124,8 @@ int amaru_nccl_unique_id(void *uid128, char *msg, int msglen);
  * everything else (result vectors, status flags) stays on NCCL. */
 int amaru_p2p_export(amaru_model *m, void *out128, char *msg, int msglen);
 int amaru_p2p_connect(amaru_model *m, const void *all_handles, const int64_t *peer_recv_start, char *msg, int msglen);
+/* collective: call with on=1 on every rank once every rank's amaru_p2p_connect returned 0 (else keep NCCL everywhere) */
+int amaru_p2p_enable(amaru_model *m, int on);
 
 int amaru_destroy(amaru_model *m);
 

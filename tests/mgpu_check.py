@@ -47,7 +47,7 @@ def main():
             out = [None] * world
             dist.all_gather_object(out, obj)
             return out
-        dm.p2p_connect(gather)
+        assert dm.p2p_connect(gather), "peer-memory path could not be enabled"
     ok = True
     ref = L.DeviceModel(flat, eqid, ndofs, nu, device=local) if rank == 0 else None
     for it in range(2):                                    # second pass: tangent on the plastic trial state
