@@ -300,8 +300,8 @@ class DeviceModel:
         ok = all(e["ok"] for e in everyone)
         if ok:
             allh = b"".join(e["handles"] for e in everyone)
-            peer_start = np.array([everyone[q]["recv_start"][everyone[q]["neigh"].index(int(v.rank))] for q in mine["neigh"]],
-                                  dtype=np.int64)
+            from .partition import peer_recv_starts
+            peer_start = peer_recv_starts(v.rank, mine["neigh"], everyone)
             hb = C.create_string_buffer(allh, len(allh))
             st = self.lib.amaru_p2p_connect(self.h, C.cast(hb, _vp), peer_start.ctypes.data_as(_i64p), self._msg, len(self._msg))
             ok = st == OK

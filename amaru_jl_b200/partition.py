@@ -125,3 +125,11 @@ def local_flat(flat: dict, eqid: np.ndarray, view: LocalView):
     out["elem_mat"] = np.ascontiguousarray(flat["elem_mat"][view.elem_gid])
     eq_local = np.ascontiguousarray(np.asarray(eqid).reshape(flat["coords"].shape[0], -1)[view.node_gid], dtype=np.int32)
     return out, eq_local
+
+
+def peer_recv_starts(rank: int, neigh, everyone) -> np.ndarray:
+    """Addressing of the peer-memory halo push (include/amaru_b200.h, amaru_p2p_connect): for every neighbour q of `rank`,
+    the first local node id — in q's numbering — of the ghost range q keeps for `rank`.  `everyone[r]` holds rank r's
+    ``neigh`` and ``recv_start`` lists (what the host all-gathers)."""
+    return np.array([everyone[int(q)]["recv_start"][list(everyone[int(q)]["neigh"]).index(int(rank))] for q in neigh],
+                    dtype=np.int64)

@@ -106,3 +106,20 @@ def test_halo_exchange_gloo_world2(tmp_path):
         procs.append(subprocess.Popen([sys.executable, str(script)], env=env))
     codes = [p.wait(timeout=180) for p in procs]
     assert codes == [0, 0]
+
+
+@pytest.mark.parametrize("nranks", [2, 4, 8])
+def test_peer_memory_halo_addressing(nranks):
+    """The peer-memory halo push writes rank p's k-th send entry for neighbour q to q's local node
+    peer_recv_start + k: that slot must be exactly the ghost copy of the same global node (amaru_p2p_connect contract)."""
+    from amaru_jl_b200.partition import peer_recv_starts
+    m = Mesh(Block([[0, 0, 0], [1, 1, 2]], nx=4, ny=4, nz=8, cellshape="HEX20"))
+    views = [partition_mesh(m.coords, m.conn, nranks, r) for r in range(nranks)]
+    everyone = [dict(neigh=[int(q) for q in v.neigh], recv_start=[int(s) for s in v.recv_start]) for v in views]
+    for p, v in enumerate(views):
+        starts = peer_recv_starts(p, v.neigh, everyone)
+        for i, q in enumerate(v.neigh):
+            sent = v.node_gid[v.send_nodes[v.send_ptr[i]:v.send_ptr[i + 1]]]
+            w = views[int(q)]
+            dst = w.node_gid[starts[i]:starts[i] + sent.size]
+            assert starts[i] >= w.nowned and np.array_equal(sent, dst)
