@@ -6,6 +6,7 @@
 // Same creation order as the reference: grid points k (outer), j, i (inner) with the serendipity points skipped; cells
 // k, j, i; local node orders of structured.jl:211-222,416-426,499-542.  Two-corner boxes with uniform spacing only.
 // Threads: node and cell loops are split over the host cores by k-planes (ids come from closed-form prefix counts).
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -203,3 +204,99 @@ int amaru_configure_dofs(int64_t nnodes, int nd, const uint8_t *prescribed, int3
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------- outer facets
+// get_outer_facets (reference src/mesh/mesh.jl:69-85): the facets seen by exactly one cell, in cell order then local
+// facet order (facet_idxs of src/shape/solids2d.jl:327,427; solids3d.jl:206,519,706).  The reference hashes every facet into
+// a Dict; here the facets are keyed by their sorted corner nodes, sorted in parallel chunks and merged.
+namespace {
+struct FacetTable {
+    int nf, nfn, nc;          // facets per cell, nodes per facet, corner nodes per facet (the first nc of each row)
+    const int *idx;           // nf x nfn, 0-based local node ids
+};
+const int F_QUAD4[] = {0, 1, 1, 2, 2, 3, 3, 0};
+const int F_QUAD8[] = {0, 1, 4, 1, 2, 5, 2, 3, 6, 3, 0, 7};
+const int F_HEX8[] = {0, 4, 7, 3, 1, 2, 6, 5, 0, 1, 5, 4, 2, 3, 7, 6, 0, 3, 2, 1, 4, 5, 6, 7};
+const int F_HEX20[] = {0, 4, 7, 3, 16, 15, 19, 11, 1, 2, 6, 5, 9, 18, 13, 17, 0, 1, 5, 4, 8, 17, 12, 16,
+                       2, 3, 7, 6, 10, 19, 14, 18, 0, 3, 2, 1, 11, 10, 9, 8, 4, 5, 6, 7, 12, 13, 14, 15};
+const int F_TET10[] = {0, 3, 2, 7, 9, 6, 0, 1, 3, 4, 8, 7, 0, 2, 1, 6, 5, 4, 1, 2, 3, 5, 9, 8};
+bool facet_table(int shape, FacetTable &t) {
+    switch (shape) {
+    case AMARU_SHAPE_QUAD4: t = {4, 2, 2, F_QUAD4}; return true;
+    case AMARU_SHAPE_QUAD8: t = {4, 3, 2, F_QUAD8}; return true;
+    case AMARU_SHAPE_HEX8: t = {6, 4, 4, F_HEX8}; return true;
+    case AMARU_SHAPE_HEX20: t = {6, 8, 4, F_HEX20}; return true;
+    case AMARU_SHAPE_TET10: t = {4, 6, 3, F_TET10}; return true;
+    }
+    return false;
+}
+struct FKey {
+    int32_t k[4];
+    int64_t id;   // cell * nf + local facet
+    bool operator<(const FKey &o) const {
+        for (int i = 0; i < 4; i++)
+            if (k[i] != o.k[i]) return k[i] < o.k[i];
+        return id < o.id;
+    }
+    bool same(const FKey &o) const { return k[0] == o.k[0] && k[1] == o.k[1] && k[2] == o.k[2] && k[3] == o.k[3]; }
+};
+}  // namespace
+
+// facet_nodes [capacity * nfn] and owner [capacity] may be NULL to count only; returns the number of outer facets (< 0: error)
+extern "C" int64_t amaru_outer_facets(int shape, int64_t nelem, const int32_t *conn, int32_t *facet_nodes, int64_t *owner,
+                                      int64_t capacity, int *nodes_per_facet) {
+    FacetTable T;
+    Grid g;
+    if (!facet_table(shape, T) || !make_grid(shape, 1, 1, 1, g) || !conn || nelem < 0) return AMARU_ERR_ARG;
+    if (nodes_per_facet) *nodes_per_facet = T.nfn;
+    const int nn = g.nn;
+    const int64_t total = nelem * T.nf;
+    std::vector<FKey> keys((size_t)total);
+    parallel_range(nelem, [&](int64_t e0, int64_t e1) {
+        for (int64_t e = e0; e < e1; e++)
+            for (int f = 0; f < T.nf; f++) {
+                FKey &K = keys[(size_t)(e * T.nf + f)];
+                for (int i = 0; i < 4; i++) K.k[i] = i < T.nc ? conn[e * nn + T.idx[f * T.nfn + i]] : -1;
+                std::sort(K.k, K.k + 4);
+                K.id = e * T.nf + f;
+            }
+    });
+    // parallel sort: sorted chunks, then pairwise merges
+    int nt = amaru_host_threads();
+    if (total < 65536) nt = 1;
+    std::vector<int64_t> cut((size_t)nt + 1);
+    for (int t = 0; t <= nt; t++) cut[(size_t)t] = total * t / nt;
+    {
+        std::vector<std::thread> th;
+        for (int t = 0; t < nt; t++) th.emplace_back([&, t] { std::sort(keys.begin() + cut[(size_t)t], keys.begin() + cut[(size_t)t + 1]); });
+        for (auto &x : th) x.join();
+    }
+    for (int step = 1; step < nt; step *= 2) {
+        std::vector<std::thread> th;
+        for (int t = 0; t + step < nt; t += 2 * step) {
+            const int64_t a = cut[(size_t)t], b = cut[(size_t)t + step], c = cut[(size_t)std::min(t + 2 * step, nt)];
+            th.emplace_back([&, a, b, c] { std::inplace_merge(keys.begin() + a, keys.begin() + b, keys.begin() + c); });
+        }
+        for (auto &x : th) x.join();
+    }
+    // facets whose key occurs once, back in (cell, local facet) order
+    std::vector<int64_t> once;
+    for (int64_t i = 0; i < total;) {
+        int64_t j = i + 1;
+        while (j < total && keys[(size_t)j].same(keys[(size_t)i])) j++;
+        if (j == i + 1) once.push_back(keys[(size_t)i].id);
+        i = j;
+    }
+    std::sort(once.begin(), once.end());
+    const int64_t nfac = (int64_t)once.size();
+    if (facet_nodes && owner) {
+        if (nfac > capacity) return AMARU_ERR_ARG;
+        for (int64_t i = 0; i < nfac; i++) {
+            const int64_t e = once[(size_t)i] / T.nf;
+            const int f = (int)(once[(size_t)i] - e * T.nf);
+            owner[i] = e;
+            for (int a = 0; a < T.nfn; a++) facet_nodes[i * T.nfn + a] = conn[e * nn + T.idx[f * T.nfn + a]];
+        }
+    }
+    return nfac;
+}

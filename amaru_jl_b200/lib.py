@@ -76,6 +76,7 @@ SYMBOLS = {
     "amaru_mesh_block_sizes": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, _i64p, _i64p, C.POINTER(C.c_int)]),
     "amaru_mesh_block": (C.c_int, [C.c_int, _dp, C.c_int, C.c_int, C.c_int, _dp, _i32p, C.c_char_p, C.c_int]),
     "amaru_configure_dofs": (C.c_int, [C.c_int64, C.c_int, _u8p, _i32p, _i64p]),
+    "amaru_outer_facets": (C.c_int64, [C.c_int, C.c_int64, _i32p, _i32p, _i64p, C.c_int64, C.POINTER(C.c_int)]),
     "amaru_newton_iteration_device": (C.c_int, [_vp, C.c_double, C.c_int, C.c_int, _dp, C.POINTER(C.c_int), _dp,
                                                 C.c_char_p, C.c_int]),
     "amaru_set_device_vectors": (C.c_int, [_vp, _dp, _dp, C.c_char_p, C.c_int]),
@@ -484,3 +485,19 @@ def configure_dofs(prescribed):
     if load().amaru_configure_dofs(p.shape[0], p.shape[1], p.ctypes.data_as(_u8p), eq.ctypes.data_as(_i32p), C.byref(nu)) != OK:
         raise AmaruError("configure_dofs!: bad arguments")
     return eq, int(nu.value)
+
+
+def outer_facets(shape_id, conn):
+    """``amaru_outer_facets``: boundary facets of a one-shape mesh -> (facet_nodes (nf, nfn) int32, owner (nf,) int64)."""
+    lib = load()
+    conn = np.ascontiguousarray(conn, dtype=np.int32)
+    nfn = C.c_int(0)
+    n = lib.amaru_outer_facets(int(shape_id), conn.shape[0], conn.ctypes.data_as(_i32p), None, None, 0, C.byref(nfn))
+    if n < 0:
+        raise AmaruError("get_outer_facets: unsupported cell shape")
+    fn = np.empty((n, nfn.value), dtype=np.int32)
+    ow = np.empty(n, dtype=np.int64)
+    n2 = lib.amaru_outer_facets(int(shape_id), conn.shape[0], conn.ctypes.data_as(_i32p), fn.ctypes.data_as(_i32p),
+                                ow.ctypes.data_as(_i64p), n, C.byref(nfn))
+    assert n2 == n
+    return fn, ow

@@ -179,10 +179,13 @@ class Mesh:
     def nelems(self):
         return self.conn.shape[0]
 
-    def outer_facets(self):
+    def outer_facets(self, native=True):
         """Boundary facets (faces in 3D, edges in 2D): those seen once (mesh.jl:69-85).
 
         -> (facet_nodes (nf, nfn) int32 in the owner's facet_idxs order, owner element (nf,))"""
+        if self._facets is None and native:
+            from . import lib as L
+            self._facets = L.outer_facets(self.shape.id, self.conn)     # C++ behind the ABI (csrc/mesher.cpp)
         if self._facets is None:
             sh = self.shape
             fl, ow = [], []

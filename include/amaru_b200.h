@@ -238,6 +238,10 @@ int amaru_write_vtu(const char *filename, const char *desc, int64_t nnodes, cons
 int amaru_mesh_block_sizes(int shape, int nx, int ny, int nz, int64_t *nnodes, int64_t *nelems, int *nn);
 int amaru_mesh_block(int shape, const double *box, int nx, int ny, int nz, double *coords /* [nnodes*3] */,
                      int32_t *conn /* [nelems*nn] */, char *msg, int msglen);
+/* get_outer_facets (src/mesh/mesh.jl:69-85): facets seen by exactly one cell, in cell order then local facet order, nodes in
+ * the owner's facet_idxs order.  Call with facet_nodes = owner = NULL to get the count; returns the count (< 0 on error). */
+int64_t amaru_outer_facets(int shape, int64_t nelem, const int32_t *conn, int32_t *facet_nodes, int64_t *owner,
+                           int64_t capacity, int *nodes_per_facet);
 /* configure_dofs! (src/bc.jl:198-233): `prescribed[nnodes*nd]` flags per (node, ux|uy|uz) -> eq ids with the unknown dofs
  * first (stable), and nu. */
 int amaru_configure_dofs(int64_t nnodes, int nd, const uint8_t *prescribed, int32_t *eqid, int64_t *nu);

@@ -50,3 +50,19 @@ def test_configure_dofs_unknowns_first_stable():
     assert nu == int((~flat).sum()) and np.array_equal(eq.reshape(-1), ref)
     eq2, nu2 = L.configure_dofs(np.zeros((5, 2), dtype=bool))
     assert nu2 == 10 and np.array_equal(eq2.reshape(-1), np.arange(10))
+
+
+@pytest.mark.parametrize("shape,n", [("QUAD4", 7), ("QUAD8", 5), ("HEX8", 6), ("HEX20", 5), ("TET10", 4), ("HEX20", 1)])
+def test_native_outer_facets_match_the_numpy_restatement(shape, n):
+    """get_outer_facets (mesh.jl:69-85): same facets, same order (cell, local facet), same node order, same owners."""
+    if shape.startswith("QUAD"):
+        b = Block([[0, 0], [1, 1]], nx=n, ny=n + 1, cellshape=shape)
+    else:
+        b = Block([[0, 0, 0], [1, 1, 1]], nx=n, ny=n + 1, nz=n + 2, cellshape=shape)
+    fn, ow = Mesh(b).outer_facets(native=False)
+    fn2, ow2 = L.outer_facets(Mesh(b).shape.id, Mesh(b).conn)
+    assert np.array_equal(fn, fn2) and np.array_equal(ow, ow2)
+    if not shape.startswith("QUAD"):                                   # closed surface: every boundary edge is shared twice
+        nx, ny, nz = n, n + 1, n + 2
+        per_cell_face = 2 if shape == "TET10" else 1
+        assert fn2.shape[0] == per_cell_face * 2 * (nx * ny + ny * nz + nx * nz)
