@@ -164,10 +164,6 @@ __global__ void k_finalize_scalars(CgScalars *scal, int stage, double tol2, int 
         else if (!(scal->acc[1] == scal->acc[1])) scal->done = 3;
     }
 }
-__global__ void k_stage_scalars(CgScalars *scal, int stage) {
-    if (stage == 1) scal->acc[0] = scal->pq;
-    else { scal->acc[0] = scal->rz_new; scal->acc[1] = scal->rr; }
-}
 
 __global__ void __launch_bounds__(ROW_THREADS)
 k_cg_pupdate(int64_t n, const double *__restrict__ z, double *p, const CgScalars *scal) {
