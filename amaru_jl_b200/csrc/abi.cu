@@ -384,7 +384,6 @@ int64_t amaru_spmv_bytes(const amaru_model *m) {
 const char *amaru_spmv_kernel(const amaru_model *m) {
     if (!m) return "";
     if (m->use_sym) return m->nd == 3 ? "k_spmv_sym<3,true>" : "k_spmv_sym<2,true>";
-    if (m->use_tma && m->blockT) return m->nd == 3 ? "k_spmv_stream2<3,true,transposed blocks>" : "k_spmv_stream2<2,true,transposed blocks>";
     if (m->use_tma) return m->spmv_ver == 2 ? (m->nd == 3 ? "k_spmv_stream2<3,true>" : "k_spmv_stream2<2,true>")
                                             : (m->nd == 3 ? "k_spmv_stream<3,true>" : "k_spmv_stream<2,true>");
     return m->nd == 3 ? "k_spmv<3,true>" : "k_spmv<2,true>";
@@ -513,7 +512,7 @@ int amaru_get_csr(amaru_model *m, int64_t *rowptr, int32_t *colind, double *val,
                 for (int32_t k = m->h_rowptr[A]; k < m->h_rowptr[A + 1]; k++) {
                     const int64_t B = m->h_col[k];
                     for (int c = 0; c < bs; c++)
-                        row.emplace_back(m->h_eqid[B * bs + c], val ? K[(size_t)k * b2 + (m->blockT ? c * bs + r : r * bs + c)] : 0.0);
+                        row.emplace_back(m->h_eqid[B * bs + c], val ? K[(size_t)k * b2 + r * bs + c] : 0.0);
                 }
                 std::sort(row.begin(), row.end(), [](const auto &x, const auto &y) { return x.first < y.first; });
                 int64_t o = cnt[(size_t)m->h_eqid[A * bs + r]];

@@ -129,9 +129,6 @@ struct amaru_model {
     int ntiles = 0, tile_blks = 0, tile_rows = 0, tile_xcap = 0, grid_tma = 0, spmv_stages = 0, spmv_warps = 0, spmv_xd = 2, spmv_sleep = 100, spmv_ver = 2;
     int64_t spmv_meta_bytes = 0;   // bytes of tile records + headers streamed per SpMV
     bool use_tma = false;
-    // EXPERIMENTAL (AMARU_BLOCK_T=1, not yet measured on a GPU): every block is stored transposed so that a consumer lane
-    // (block, c) reads column c as contiguous doubles and only its own x_j[c]
-    bool blockT = false;
     // symmetric-storage SpMV of the CG loop (spmv.cu): upper-triangular blocks (col >= row; every owned x ghost block)
     bool use_sym = false;
     int64_t nublk = 0;             // stored upper blocks

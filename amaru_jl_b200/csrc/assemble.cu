@@ -46,7 +46,6 @@ struct AsmArgs {
     double *K;
     int *status;
     int64_t e_begin, e_end;  // colour-sorted element range of this launch
-    int transposed;          // store every block transposed (amaru_model::blockT)
 };
 
 template <int NN, int ND, int NIP, int EPB, int NT>
@@ -178,9 +177,7 @@ __global__ void __launch_bounds__(NT) k_assemble_K(AsmArgs p) {
         if (dst >= 0) {
             double *Kb = p.K + (int64_t)dst * BS2;
 #pragma unroll
-            for (int r = 0; r < ND; r++)
-#pragma unroll
-                for (int c = 0; c < ND; c++) Kb[p.transposed ? c * ND + r : r * ND + c] += acc[r * ND + c];
+            for (int k = 0; k < BS2; k++) Kb[k] += acc[k];
         }
     }
 }
@@ -276,7 +273,6 @@ void launch_K(amaru_model *m, Batch &b) {
     a.mat_kind = m->d_mat_kind; a.mat_par = m->d_mat_par; a.dNdR = b.d_dNdR; a.w = b.d_w;
     a.state = m->d_state; a.nip_total = m->nip_total; a.ip_off = b.ip_off; a.th = m->th;
     a.K = m->d_K; a.status = m->d_status;
-    a.transposed = m->blockT ? 1 : 0;   // the mass blocks are multiples of the identity: nothing to transpose there
     for (size_t c = 0; c + 1 < b.color_off.size(); c++) {
         a.e_begin = b.color_off[c];
         a.e_end = b.color_off[c + 1];

@@ -349,7 +349,7 @@ k_spmv_stream(int ntiles, const SpmvTile *__restrict__ tiles, const int32_t *__r
 // is executed once per tile instead of once per consumer warp.
 constexpr int STREAM2_THREADS = (NCW + 2) * 32;
 
-template <int BS, bool DOT, bool TB = false>   // TB: blocks stored transposed (experimental, amaru_model::blockT)
+template <int BS, bool DOT>
 __global__ void __launch_bounds__(STREAM2_THREADS)
 k_spmv_stream2(int ntiles, const SpmvTile *__restrict__ tiles, const int32_t *__restrict__ trec,
                const double *__restrict__ A, const double *__restrict__ x, double *__restrict__ y, int mask_rows,
@@ -490,33 +490,10 @@ k_spmv_stream2(int ntiles, const SpmvTile *__restrict__ tiles, const int32_t *__
             for (int lr = warp; lr < h_nrows; lr += NCW) {
                 const int32_t e0 = rec[lr], e1 = rec[lr + 1];
                 const int k0 = e0 & 0xffff, nbr = (e1 & 0xffff) - k0;
-                double acc0 = 0.0, acc1 = 0.0;
-                if constexpr (TB) {
-                    // lane (b, c): COLUMN c of the block (3 contiguous doubles in the transposed storage) times its own
-                    // x_j[c]; accumulator k collects row (c + k) mod BS, so that after the steps of the row the lane of
-                    // component r completes S_r = sum_c a_r(b, c) with BS-1 shuffles inside the block's lanes
-                    double a[BS];
-#pragma unroll
-                    for (int j = 0; j < BS; j++) a[j] = 0.0;
-                    if (act) {
-                        const double *pv = sval + (k0 + b) * B2 + r * BS;
-                        const uint16_t *pl = sl + k0 + b;
-                        for (int k = b; k < nbr; k += BPS) {
-                            const double xc = sx[pl[0] + r];
-#pragma unroll
-                            for (int j = 0; j < BS; j++) a[j] += pv[(r + j) % BS] * xc;
-                            pl += BPS;
-                            pv += BPS * B2;
-                        }
-                    }
-                    acc0 = a[0];
-#pragma unroll
-                    for (int j = 1; j < BS; j++)
-                        acc0 += __shfl_sync(0xffffffffu, a[BS - j], act ? b * BS + (r + j) % BS : lane);
-                } else {
                 const double *pv = sval + (k0 + b) * B2 + r * BS;
                 const uint16_t *pl = sl + k0 + b;
                 const int nfull = nbr / BPS, rem = nbr - nfull * BPS;
+                double acc0 = 0.0, acc1 = 0.0;
                 if (act) {
                     int s = 0;
                     for (; s + 2 <= nfull; s += 2) {
@@ -541,7 +518,6 @@ k_spmv_stream2(int ntiles, const SpmvTile *__restrict__ tiles, const int32_t *__
 #pragma unroll
                         for (int j = 0; j < BS; j++) acc1 += pv[j] * x0[j];
                     }
-                }
                 }
                 double tot = acc0 + acc1;
                 if constexpr (BS == 3) {
@@ -932,11 +908,7 @@ template <int BS, bool DOT>
 void launch_stream(amaru_model *m, const double *A, const double *x, double *y, int mask, int check_done, int finalize) {
     const StageLayout L = stage_layout(BS, m->tile_blks, m->tile_rows, m->tile_xcap);
     const size_t smem = m->spmv_stages * L.vbytes + (size_t)(m->spmv_stages + m->spmv_xd) * (L.rbytes + L.xbytes);
-    if (m->spmv_ver == 2 && m->blockT)
-        k_spmv_stream2<BS, DOT, true><<<m->grid_tma, STREAM2_THREADS, smem, m->stream>>>(
-            m->ntiles, reinterpret_cast<const SpmvTile *>(m->d_tiles), m->d_tmeta, A, x, y, mask, m->tile_blks, m->tile_rows,
-            m->tile_xcap, m->spmv_stages, m->spmv_xd, m->spmv_sleep, m->d_partial, m->d_scal, check_done, finalize);
-    else if (m->spmv_ver == 2)
+    if (m->spmv_ver == 2)
         k_spmv_stream2<BS, DOT><<<m->grid_tma, STREAM2_THREADS, smem, m->stream>>>(
             m->ntiles, reinterpret_cast<const SpmvTile *>(m->d_tiles), m->d_tmeta, A, x, y, mask, m->tile_blks, m->tile_rows,
             m->tile_xcap, m->spmv_stages, m->spmv_xd, m->spmv_sleep, m->d_partial, m->d_scal, check_done, finalize);
@@ -955,8 +927,6 @@ bool configure_stream(amaru_model *m) {
     if (m->spmv_ver == 2) {
         CUDA_CHECK(cudaFuncSetAttribute(k_spmv_stream2<BS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         CUDA_CHECK(cudaFuncSetAttribute(k_spmv_stream2<BS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CUDA_CHECK(cudaFuncSetAttribute(k_spmv_stream2<BS, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CUDA_CHECK(cudaFuncSetAttribute(k_spmv_stream2<BS, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_spmv_stream2<BS, true>, STREAM2_THREADS, smem));
     } else {
         CUDA_CHECK(cudaFuncSetAttribute(k_spmv_stream<BS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1191,9 +1161,7 @@ void amaru_spmv_setup(amaru_model *m) {
     CUDA_CHECK(cudaMemcpy(m->d_tmeta, trec.data(), trec.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
     m->spmv_meta_bytes = (int64_t)moff * 4 + (int64_t)nt * sizeof(SpmvTile);
     m->use_tma = (bs == 3) ? configure_stream<3>(m) : configure_stream<2>(m);
-    // experimental transposed block storage: only the v2 streamed kernel knows it (the flag is fixed before the first assembly)
-    m->blockT = env_int("AMARU_BLOCK_T", 0) != 0 && m->use_tma && m->spmv_ver == 2;
-    if (!m->blockT) setup_sym(m);
+    setup_sym(m);
 }
 
 // y = A x on the owned rows (+ p·Ap partial dot and CG scalar finalisation when dot != 0)

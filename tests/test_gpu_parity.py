@@ -451,35 +451,3 @@ def test_edge_cases_single_element_all_prescribed_empty_sets():
     dFo, st = om.update_state(Uo)
     assert st == 0 and rel(dF, dFo) < 1e-12
     dm.close()
-
-
-@pytest.mark.skipif(__import__("os").environ.get("AMARU_TEST_EXPERIMENTAL", "0") != "1",
-                    reason="experimental transposed-block SpMV (AMARU_BLOCK_T=1) has not been measured on a GPU yet; "
-                           "set AMARU_TEST_EXPERIMENTAL=1 to run")
-@pytest.mark.parametrize("shape,n", [("QUAD8", 6), ("HEX8", 5), ("HEX20", 4), ("TET10", 3)])
-def test_transposed_block_storage_matches_default(shape, n, monkeypatch):
-    """AMARU_BLOCK_T=1: blocks stored transposed, consumer lane = (block, column).  Same CSR at the
-    ABI, same products, same solve as the default layout."""
-    model = make_model(shape, n, "vm0" if shape != "QUAD8" else "vm", jitter=0.15, seed=3)
-    eqid, nu, setup = model.configure_dofs(clamp_bcs(model))
-    Uex, Fex = model.get_bc_vals(eqid, setup)
-    x = np.random.default_rng(2).normal(size=eqid.size)
-    out = {}
-    for flag in ("1", "0"):
-        monkeypatch.setenv("AMARU_BLOCK_T", flag)
-        dm = L.DeviceModel(model.flatten(), eqid, eqid.size, nu)
-        try:
-            assert ("transposed" in dm.spmv_kernel) == (flag == "1")
-            dm.assemble_K()
-            U, F = Uex.copy(), Fex.copy()
-            iters, _ = dm.solve(U, F, cg_rtol=1e-12)
-            dm.update_state(3.0 * U)
-            dm.assemble_K()                                             # unsymmetric-looking blocks on the plastic tangent
-            rp, ci, val = dm.get_csr()
-            out[flag] = dict(U=U, F=F, iters=iters, rp=rp, ci=ci, val=val, Kx=dm.matvec(1.0, 0.0, x))
-        finally:
-            dm.close()
-    a, b = out["1"], out["0"]
-    assert np.array_equal(a["rp"], b["rp"]) and np.array_equal(a["ci"], b["ci"]) and np.array_equal(a["val"], b["val"])
-    assert rel(a["Kx"], b["Kx"]) < 1e-13 and rel(a["U"], b["U"]) < 1e-9 and rel(a["F"][nu:], b["F"][nu:]) < 1e-9
-    assert abs(a["iters"] - b["iters"]) <= max(2, b["iters"] // 50)
