@@ -232,6 +232,7 @@ amaru_model *create_impl(const CreateArgs &a) {
     CUDA_CHECK(cudaMemset(m->d_F, 0, (size_t)m->ndofs * sizeof(double)));
     CUDA_CHECK(cudaMalloc(&m->d_status, sizeof(int)));
     CUDA_CHECK(cudaMemset(m->d_status, 0, sizeof(int)));
+    amaru_ebe_setup(m);
     amaru_pcg_setup(m);
     CUDA_CHECK(cudaStreamSynchronize(m->stream));
     return mp.release();
@@ -242,6 +243,7 @@ void free_model(amaru_model *m) {
     if (m->stream) cudaStreamSynchronize(m->stream);
     amaru_comm_destroy(m);
     amaru_recovery_destroy(m);
+    amaru_ebe_destroy(m);
     for (Batch &B : m->batches) {
         cudaFree(B.d_conn); cudaFree(B.d_emat); cudaFree(B.d_map); cudaFree(B.d_perm); cudaFree(B.d_owned);
         cudaFree(B.d_rho); cudaFree(B.d_dNdR); cudaFree(B.d_N); cudaFree(B.d_w);
@@ -375,6 +377,7 @@ int64_t amaru_launch_count(const amaru_model *m) { return m ? m->launches : -1; 
 int64_t amaru_spmv_bytes(const amaru_model *m) {
     if (!m) return -1;
     const int64_t b2 = (int64_t)m->nd * m->nd, n = m->nowned * m->nd;
+    if (m->op_ebe) return amaru_ebe_bytes(m);
     if (m->use_sym)   // CG product from the symmetric storage: upper blocks + records + x once + y zeroed and reduced into once
         return m->nublk * b2 * 8 + m->sym_meta_bytes + 8 * n + 16 * n;
     const int64_t meta = m->use_tma ? m->spmv_meta_bytes : m->nblk * 4 + (m->nowned + 1) * 4 + n;   // + fixed mask
@@ -383,6 +386,7 @@ int64_t amaru_spmv_bytes(const amaru_model *m) {
 
 const char *amaru_spmv_kernel(const amaru_model *m) {
     if (!m) return "";
+    if (m->op_ebe) return amaru_ebe_kernel(m);
     if (m->use_sym) return m->nd == 3 ? "k_spmv_sym<3,true>" : "k_spmv_sym<2,true>";
     if (m->use_tma) return m->spmv_ver == 2 ? (m->nd == 3 ? "k_spmv_stream2<3,true>" : "k_spmv_stream2<2,true>")
                                             : (m->nd == 3 ? "k_spmv_stream<3,true>" : "k_spmv_stream<2,true>");
@@ -445,6 +449,7 @@ int amaru_assemble_K(amaru_model *m, char *msg, int msglen) {
         reset_status(m);
         amaru_launch_assemble(m, 0);
         amaru_combine_matrix(m);
+        amaru_ebe_refresh(m);
         if (m->nranks > 1) amaru_allreduce_max_int(m, m->d_status);
         const int st = read_status(m);
         if (st) throw AmaruError{st, status_text(st)};
@@ -604,6 +609,24 @@ int amaru_matvec(amaru_model *m, double a, double b, const double *x, double *y,
     });
 }
 
+int amaru_operator_apply(amaru_model *m, const double *x, double *y, int masked, double *pAp, char *msg, int msglen) {
+    return guarded(msg, msglen, [&]() {
+        AMARU_REQUIRE(m && x && y, AMARU_ERR_ARG, "null argument");
+        use_device(m);
+        const size_t bytes = (size_t)m->ndofs * sizeof(double);
+        CUDA_CHECK(cudaMemcpyAsync(m->d_U, x, bytes, cudaMemcpyHostToDevice, m->stream));
+        amaru_eq_to_nodes(m, m->d_U, m->d_p);
+        const double pq = amaru_operator_product(m, masked);
+        if (pAp) *pAp = pq;
+        CUDA_CHECK(cudaMemsetAsync(m->d_F, 0, bytes, m->stream));
+        amaru_nodes_to_eq(m, m->d_q, m->d_F, 0);
+        if (m->nranks > 1) amaru_allreduce_sum(m, m->d_F, m->ndofs);
+        CUDA_CHECK(cudaMemcpyAsync(y, m->d_F, bytes, cudaMemcpyDeviceToHost, m->stream));
+        CUDA_CHECK(cudaStreamSynchronize(m->stream));
+        return AMARU_OK;
+    });
+}
+
 int amaru_set_device_vectors(amaru_model *m, const double *U, const double *F, char *msg, int msglen) {
     return guarded(msg, msglen, [&]() {
         AMARU_REQUIRE(m && U && F, AMARU_ERR_ARG, "null argument");
@@ -630,6 +653,7 @@ int amaru_newton_iteration_device(amaru_model *m, double cg_rtol, int cg_maxit, 
         reset_status(m);
         amaru_launch_assemble(m, 0);                                   // mount_K            (mech-solver.jl:327)
         amaru_combine_matrix(m);
+        amaru_ebe_refresh(m);
         if (m->nranks > 1) amaru_allreduce_max_int(m, m->d_status);
         const int as = read_status(m);                                 // assembly status (update_device resets the flag)
         CUDA_CHECK(cudaEventRecord(ev[1], m->stream));
@@ -686,6 +710,12 @@ int amaru_time_kernel(amaru_model *m, int kind, int precond, int reps, double *a
         cudaEventDestroy(e1);
         return AMARU_OK;
     });
+}
+
+int amaru_set_operator(amaru_model *m, int kind) {
+    if (!m || (kind != AMARU_OPERATOR_CSR && kind != AMARU_OPERATOR_EBE)) return AMARU_ERR_ARG;
+    m->op_ebe = kind == AMARU_OPERATOR_EBE;
+    return AMARU_OK;
 }
 
 int amaru_set_profiling(amaru_model *m, int on) {

@@ -148,6 +148,10 @@ struct amaru_model {
     void *recovery = nullptr;      // Recovery*
     bool recovery_vm_first = true;
 
+    // matrix-free tangent operator of the CG loop (ebe.cu)
+    void *ebe = nullptr;           // Ebe*
+    bool op_ebe = true;            // CG products: element-by-element (default) or block-CSR SpMV (AMARU_OPERATOR=csr)
+
     bool cg_graph = true;          // replay the CG batches as a CUDA graph on one GPU (AMARU_CG_GRAPH=0 disables)
 
     // bookkeeping
@@ -189,7 +193,17 @@ void amaru_combine_matrix(amaru_model *m);                            // pcg.cu:
 int amaru_check_nan(amaru_model *m, const double *d_v, int64_t n);    // pcg.cu
 void amaru_zero_free(amaru_model *m, double *x);                     // pcg.cu
 void amaru_axpby(amaru_model *m, int64_t n, double a, const double *x, double b, const double *y, double *out);  // pcg.cu
+double amaru_operator_product(amaru_model *m, int masked);           // pcg.cu: d_q = A d_p with the CG operator (+ p.Ap)
 void amaru_time_cg_kernel(amaru_model *m, int kind, int precond, int reps);  // pcg.cu
+
+// matrix-free operator (ebe.cu)
+void amaru_ebe_setup(amaru_model *m);
+void amaru_ebe_destroy(amaru_model *m);
+void amaru_ebe_refresh(amaru_model *m);                               // tangent planes <- current IP state
+void amaru_ebe_set_owned(amaru_model *m, int batch, const uint8_t *h_owned_sorted);
+void amaru_ebe_apply(amaru_model *m, const double *x, double *y, int mask, int dot, int check_done, int finalize);
+int64_t amaru_ebe_bytes(const amaru_model *m);
+const char *amaru_ebe_kernel(const amaru_model *m);
 
 // halo exchange (halo.cu) — no-ops for nranks == 1
 void amaru_halo_exchange(amaru_model *m, double *d_v);

@@ -1,0 +1,560 @@
+// K13: matrix-free (element-by-element) tangent operator  y = (a·K + b·M) x  (+ fused p·Ap) for the PCG that replaces
+// lu(K11) (reference src/solver.jl:38-43).  K is the matrix mount_K builds (src/mech/mech-solver.jl:78-110 with
+// elem_stiffness, src/mech/elem/mech-solid.jl:124-166); instead of streaming its 18 KB per HEX20 element every CG
+// iteration (block-CSR SpMV, spmv.cu) the product is re-integrated from 80-128 bytes per integration point:
+//
+//   per IP (constant over the analysis, small strains): J⁻¹ (nd² doubles) and coef = detJ·w·th
+//   per IP (refreshed by amaru_assemble_K):             w (6 doubles) with  D = De − w wᵀ
+//
+// All three materials of the path have a tangent of that form (associated flow): von Mises  w = De·n/√(n·De·n + √1.5·H)
+// (von-mises.jl:112-125), Drucker–Prager  w = De·V/√(|V|·(V·De·V/|V| + H)) (drucker-prager.jl:86-109), elastic w = 0.
+// With G = Σ_a x_a ⊗ ∂N_a/∂R the displacement gradient is H = G·J⁻¹, ε = sym(H) in Mandel order (setB,
+// mech-solid.jl:82-121), σ = coef·a·D·ε, and the nodal force is f_a = Σ_q ∂N_a/∂R(q) · S(q) with S = J⁻¹·T(σ): the shape
+// table is shared by all elements, so both contractions are small GEMMs against a constant operand held in shared memory.
+//
+// One CTA works on groups of NT/NIP elements of ONE colour (elements of a colour share no node: plain read-modify-write of
+// y, fixed order, no atomics — same determinism argument as assemble.cu):
+//   phase 1  gather x of the group's nodes                       (thread = element-node)
+//   phase 2  G, H, ε, σ, S and the energy coef·εᵀDε              (thread = element × integration point)
+//   phase 3  f_a = Σ_q,k dN[q][k][a]·S[q][k][:], y[node] += f_a   (thread = element × TA nodes, register tile TA×nd)
+// p·Ap = Σ_e Σ_q coef·εᵀDε over the elements this rank owns (p vanishes on prescribed dofs, so this is the masked dot);
+// partial sums are combined in a fixed order by the last block of every colour launch.
+//
+// Algorithmic bytes per application: 8·(nd²+1)·nip + 48·nip(plastic elements) + 4·nn·nelem + 8n + 8n.
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+
+#include "materials.cuh"
+#include "reduce.cuh"
+
+namespace {
+
+constexpr int EBE_NT = 256;
+
+struct EbeBatch {          // per element batch, colour-sorted element order (same order as the IP state planes)
+    double *d_geo = nullptr;      // [(nd*nd+1)][nipb]: J⁻¹ row-major planes, then coef
+    uint8_t *d_pflag = nullptr;   // [nelem] 1 = some IP of the element has w != 0
+    uint8_t *d_eown = nullptr;    // [nelem] 1 = this rank owns the element (counts in p·Ap); nullptr = all owned
+    int grid = 1;
+};
+
+struct Ebe {
+    std::vector<EbeBatch> b;
+    double *d_w = nullptr;        // [6][nip_total]
+    double *d_dog = nullptr;      // [nmats][3]: c(1-ν), cν, c(1-2ν)
+    int64_t *d_nplastic = nullptr;   // device counter of flagged elements (for the byte count)
+    int64_t nplastic_ip = 0;
+};
+
+struct EbeArgs {
+    const int32_t *conn;
+    const int32_t *emat;
+    const uint8_t *eown;
+    const uint8_t *pflag;
+    const double *dog;
+    const double *geo;
+    int64_t nipb;
+    const double *w;
+    int64_t nip_total, ip_off;
+    const double *dNdR;     // [NIP][NN][ND] (Batch::d_dNdR)
+    const double *Nf;       // [NIP][NN]
+    const double *rho;      // [nelem] (mass term) or nullptr
+    double sa, sb;
+    const double *x;
+    double *y;
+    const uint8_t *fixed;
+    int mask;
+    int64_t nowned;
+    int64_t e_begin, e_end;
+    double *partial;
+    CgScalars *scal;
+    int dot, first, last, finalize, check_done;
+};
+
+template <int NN, int ND, int NIP, int TA, bool MASS>
+struct EbeLayout {
+    static constexpr int EPB = EBE_NT / NIP;
+    static constexpr int QS = (ND * NN) | 1;                 // stride of one integration point in the dN table (odd)
+    static constexpr int US = (NN * ND) | 1;                 // stride of one element in the x stage (odd)
+    static constexpr int SQ = ND * ND + (MASS ? ND : 0);     // S (+ mass vector) of one integration point
+    static constexpr int ES = (NIP * SQ) | 1;                // stride of one element in the S stage (odd)
+    static constexpr int NTH3 = NN / TA;                     // phase-3 threads per element
+    static constexpr size_t doubles = (size_t)NIP * QS + (MASS ? NIP * NN : 0) + (size_t)EPB * US + (size_t)EPB * ES;
+    static constexpr size_t bytes = doubles * 8 + (size_t)EPB * NN * 4;
+    static_assert(NN % TA == 0, "TA must divide NN");
+    static_assert(EPB * NTH3 <= EBE_NT, "phase 3 needs more threads than the CTA has");
+};
+
+template <int NN, int ND, int NIP, int TA, bool MASS>
+__global__ void __launch_bounds__(EBE_NT) k_ebe_apply(EbeArgs p) {
+    if (p.check_done && p.scal->done) return;
+    using L = EbeLayout<NN, ND, NIP, TA, MASS>;
+    constexpr int EPB = L::EPB, QS = L::QS, US = L::US, SQ = L::SQ, ES = L::ES, NTH3 = L::NTH3;
+    extern __shared__ __align__(16) double esm[];
+    double *sdN = esm;                                   // [NIP][QS]: dN[q][k][a] at q*QS + k*NN + a
+    double *sNf = sdN + NIP * QS;                        // [NIP][NN] (mass only)
+    double *sU = sNf + (MASS ? NIP * NN : 0);            // [EPB][US]: x of element-node (a, i) at e*US + a*ND + i
+    double *sS = sU + EPB * US;                          // [EPB][ES]: S[q][k][i] at e*ES + q*SQ + k*ND + i
+    int32_t *sNode = reinterpret_cast<int32_t *>(sS + EPB * ES);   // [EPB][NN]
+    const int tid = threadIdx.x;
+    for (int i = tid; i < NIP * NN * ND; i += EBE_NT) {   // global table is [q][a][k]
+        const int q = i / (NN * ND), r = i - q * NN * ND, a = r / ND, k = r - a * ND;
+        sdN[q * QS + k * NN + a] = p.dNdR[i];
+    }
+    if (MASS)
+        for (int i = tid; i < NIP * NN; i += EBE_NT) sNf[i] = p.Nf[i];
+    double dsum[1] = {0.0};
+    const int64_t ngroups = (p.e_end - p.e_begin + EPB - 1) / EPB;
+    for (int64_t g = blockIdx.x; g < ngroups; g += gridDim.x) {
+        const int64_t e0 = p.e_begin + g * EPB;
+        const int ne = (int)min((int64_t)EPB, p.e_end - e0);
+        __syncthreads();   // previous group's phase 3 is done with sS / sNode (and the tables are staged)
+        // ---- phase 1: x of the group's element nodes
+        for (int i = tid; i < ne * NN; i += EBE_NT) {
+            const int e = i / NN, a = i - e * NN;
+            const int32_t node = p.conn[e0 * NN + i];
+            sNode[i] = node;
+#pragma unroll
+            for (int d = 0; d < ND; d++) sU[e * US + a * ND + d] = p.x[(int64_t)node * ND + d];
+        }
+        __syncthreads();
+        // ---- phase 2: one thread per (element, integration point)
+        {
+            const int e = tid / NIP, q = tid - e * NIP;
+            if (e < ne) {
+                const int64_t ipb = (e0 + e) * NIP + q;              // position inside the batch's planes
+                double G[ND * ND];
+#pragma unroll
+                for (int k = 0; k < ND * ND; k++) G[k] = 0.0;
+                double ub[ND];
+#pragma unroll
+                for (int d = 0; d < ND; d++) ub[d] = 0.0;
+                const double *U = sU + e * US, *dn = sdN + q * QS;
+#pragma unroll 4
+                for (int a = 0; a < NN; a++) {
+                    double u[ND], d_[ND];
+#pragma unroll
+                    for (int i = 0; i < ND; i++) u[i] = U[a * ND + i];
+#pragma unroll
+                    for (int k = 0; k < ND; k++) d_[k] = dn[k * NN + a];
+#pragma unroll
+                    for (int i = 0; i < ND; i++)
+#pragma unroll
+                        for (int k = 0; k < ND; k++) G[i * ND + k] += u[i] * d_[k];
+                    if (MASS) {
+                        const double n = sNf[q * NN + a];
+#pragma unroll
+                        for (int i = 0; i < ND; i++) ub[i] += n * u[i];
+                    }
+                }
+                double Ji[ND * ND];
+#pragma unroll
+                for (int k = 0; k < ND * ND; k++) Ji[k] = p.geo[(int64_t)k * p.nipb + ipb];
+                const double coef = p.geo[(int64_t)(ND * ND) * p.nipb + ipb];
+                double H[ND * ND];
+#pragma unroll
+                for (int i = 0; i < ND; i++)
+#pragma unroll
+                    for (int j = 0; j < ND; j++) {
+                        double v = 0.0;
+#pragma unroll
+                        for (int k = 0; k < ND; k++) v += G[i * ND + k] * Ji[k * ND + j];
+                        H[i * ND + j] = v;
+                    }
+                double ep[6], sg[6];
+                if constexpr (ND == 3) {
+                    ep[0] = H[0]; ep[1] = H[4]; ep[2] = H[8];
+                    ep[3] = (H[5] + H[7]) / AM_SR2; ep[4] = (H[2] + H[6]) / AM_SR2; ep[5] = (H[1] + H[3]) / AM_SR2;
+                } else {
+                    ep[0] = H[0]; ep[1] = H[3]; ep[2] = 0.0; ep[3] = 0.0; ep[4] = 0.0; ep[5] = (H[1] + H[2]) / AM_SR2;
+                }
+                const double *dg = p.dog + 3 * p.emat[e0 + e];
+                const double dd = dg[0], oo = dg[1], gg = dg[2];
+                sg[0] = dd * ep[0] + oo * ep[1] + oo * ep[2];
+                sg[1] = oo * ep[0] + dd * ep[1] + oo * ep[2];
+                sg[2] = oo * ep[0] + oo * ep[1] + dd * ep[2];
+                sg[3] = gg * ep[3]; sg[4] = gg * ep[4]; sg[5] = gg * ep[5];
+                if (p.pflag[e0 + e]) {
+                    const int64_t ip = p.ip_off + ipb;
+                    double w[6], t = 0.0;
+#pragma unroll
+                    for (int c = 0; c < 6; c++) {
+                        w[c] = p.w[(int64_t)c * p.nip_total + ip];
+                        t += w[c] * ep[c];
+                    }
+#pragma unroll
+                    for (int c = 0; c < 6; c++) sg[c] -= w[c] * t;
+                }
+                const double ca = coef * p.sa;
+                double en = 0.0;
+#pragma unroll
+                for (int c = 0; c < 6; c++) {
+                    sg[c] *= ca;
+                    en += ep[c] * sg[c];
+                }
+                double *S = sS + e * ES + q * SQ;
+                if constexpr (ND == 3) {
+                    const double T[9] = {sg[0], sg[5] / AM_SR2, sg[4] / AM_SR2, sg[5] / AM_SR2, sg[1], sg[3] / AM_SR2,
+                                         sg[4] / AM_SR2, sg[3] / AM_SR2, sg[2]};
+#pragma unroll
+                    for (int k = 0; k < 3; k++)
+#pragma unroll
+                        for (int i = 0; i < 3; i++) S[k * 3 + i] = Ji[k * 3] * T[i * 3] + Ji[k * 3 + 1] * T[i * 3 + 1] + Ji[k * 3 + 2] * T[i * 3 + 2];
+                } else {
+                    const double T[4] = {sg[0], sg[5] / AM_SR2, sg[5] / AM_SR2, sg[1]};
+#pragma unroll
+                    for (int k = 0; k < 2; k++)
+#pragma unroll
+                        for (int i = 0; i < 2; i++) S[k * 2 + i] = Ji[k * 2] * T[i * 2] + Ji[k * 2 + 1] * T[i * 2 + 1];
+                }
+                if (MASS) {
+                    const double cm = coef * p.sb * p.rho[e0 + e];
+#pragma unroll
+                    for (int i = 0; i < ND; i++) {
+                        S[ND * ND + i] = cm * ub[i];
+                        en += cm * ub[i] * ub[i];
+                    }
+                }
+                if (p.dot && (p.eown == nullptr || p.eown[e0 + e])) dsum[0] += en;
+            }
+        }
+        __syncthreads();
+        // ---- phase 3: one thread per (element, TA nodes): f_a = Σ_q Σ_k dN[q][k][a]·S[q][k][:] (+ N_a(q)·m(q))
+        if (tid < ne * NTH3) {
+            const int e = tid / NTH3, a0 = (tid - e * NTH3) * TA;
+            double f[TA][ND];
+#pragma unroll
+            for (int t = 0; t < TA; t++)
+#pragma unroll
+                for (int i = 0; i < ND; i++) f[t][i] = 0.0;
+            const double *S = sS + e * ES;
+#pragma unroll 2
+            for (int q = 0; q < NIP; q++) {
+#pragma unroll
+                for (int k = 0; k < ND; k++) {
+                    double s[ND], d_[TA];
+#pragma unroll
+                    for (int i = 0; i < ND; i++) s[i] = S[q * SQ + k * ND + i];
+#pragma unroll
+                    for (int t = 0; t < TA; t++) d_[t] = sdN[q * QS + k * NN + a0 + t];
+#pragma unroll
+                    for (int t = 0; t < TA; t++)
+#pragma unroll
+                        for (int i = 0; i < ND; i++) f[t][i] += d_[t] * s[i];
+                }
+                if (MASS) {
+                    double mv[ND];
+#pragma unroll
+                    for (int i = 0; i < ND; i++) mv[i] = S[q * SQ + ND * ND + i];
+#pragma unroll
+                    for (int t = 0; t < TA; t++) {
+                        const double n = sNf[q * NN + a0 + t];
+#pragma unroll
+                        for (int i = 0; i < ND; i++) f[t][i] += n * mv[i];
+                    }
+                }
+            }
+#pragma unroll
+            for (int t = 0; t < TA; t++) {
+                const int64_t node = sNode[e * NN + a0 + t];
+                if (node < p.nowned) {   // ghost rows belong to the neighbour rank (it integrates the element too)
+#pragma unroll
+                    for (int i = 0; i < ND; i++) {
+                        const int64_t k = node * ND + i;
+                        if (!(p.mask && p.fixed[k])) p.y[k] += f[t][i];
+                    }
+                }
+            }
+        }
+    }
+    if (p.dot) {
+        block_sum<1, EBE_NT>(dsum);
+        if (publish_partials<1>(dsum, p.partial, &p.scal->counter[0])) {
+            sum_partials<1, EBE_NT>(dsum, p.partial);
+            if (threadIdx.x == 0) {
+                const double acc = p.first ? dsum[0] : p.scal->pq + dsum[0];   // colours are summed in launch order
+                p.scal->pq = acc;
+                p.scal->acc[0] = acc;   // multi-GPU: all-reduced in place after the last colour
+                if (p.last && p.finalize) {
+                    if (!(acc > 0.0)) p.scal->done = 3;   // not SPD / breakdown
+                    p.scal->alpha = p.scal->rz_old / acc;
+                }
+            }
+        }
+    }
+}
+
+// J⁻¹ and coef = detJ·w·th of every integration point (once per handle: the geometry does not change)
+template <int NN, int ND, int NIP>
+__global__ void k_ebe_geometry(int64_t nelem, const int32_t *__restrict__ conn, const double *__restrict__ coords,
+                               const double *__restrict__ dNdR, const double *__restrict__ wq, double th, double *geo,
+                               int64_t nipb) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nelem * NIP; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t e = i / NIP;
+        const int q = (int)(i - e * NIP);
+        double X[NN * ND];
+        for (int a = 0; a < NN; a++) {
+            const int64_t node = conn[e * NN + a];
+#pragma unroll
+            for (int d = 0; d < ND; d++) X[a * ND + d] = coords[node * 3 + d];
+        }
+        double Ji[ND * ND];
+        const double det = am_jacobian<NN, ND>(X, dNdR + q * NN * ND, Ji);
+#pragma unroll
+        for (int k = 0; k < ND * ND; k++) geo[(int64_t)k * nipb + i] = Ji[k];
+        geo[(int64_t)(ND * ND) * nipb + i] = det * wq[q] * th;
+    }
+}
+
+// w of every integration point from the current IP state (calcD of the three materials in rank-one form)
+__global__ void k_ebe_tangent(int nip, int64_t nelem, int64_t ip_off, int64_t nip_total, const int32_t *__restrict__ emat,
+                              const int32_t *__restrict__ mat_kind, const double *__restrict__ mat_par,
+                              const double *__restrict__ state, double *w, uint8_t *pflag) {
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < nelem; e += (int64_t)gridDim.x * blockDim.x) {
+        const MatPar mp = load_mat(mat_kind, mat_par, emat[e]);
+        int any = 0;
+        for (int q = 0; q < nip; q++) {
+            const int64_t ip = ip_off + e * nip + q;
+            double wv[6] = {0, 0, 0, 0, 0, 0};
+            const double dlam = state[(int64_t)13 * nip_total + ip];
+            if (mp.kind != AMARU_MAT_LINEAR_ELASTIC && dlam != 0.0) {
+                double sig[6];
+#pragma unroll
+                for (int c = 0; c < 6; c++) sig[c] = state[(int64_t)c * nip_total + ip];
+                if (mp.kind == AMARU_MAT_VON_MISES) {
+                    if (am_J2(sig) > 0.0) {   // the assembly kernel reports the failing case (von-mises.jl:117)
+                        double s[6], n[6], Dn[6];
+                        am_dev(sig, s);
+                        const double ns = am_norm(s);
+#pragma unroll
+                        for (int i = 0; i < 6; i++) n[i] = sqrt(1.5) * s[i] / ns;
+                        am_De_mul(mp.E, mp.nu, n, Dn);
+                        double den = 0.0;
+#pragma unroll
+                        for (int i = 0; i < 6; i++) den += n[i] * Dn[i];
+                        den -= sqrt(1.5) * (-mp.p3);
+                        const double sc = 1.0 / sqrt(den);
+#pragma unroll
+                        for (int i = 0; i < 6; i++) wv[i] = Dn[i] * sc;
+                        any = 1;
+                    }
+                } else {
+                    const double alpha = mp.p2, H = mp.p4;
+                    double V[6];
+                    if (am_J2(sig) != 0.0) {
+                        double s[6];
+                        am_dev(sig, s);
+                        const double ns = am_norm(s);
+#pragma unroll
+                        for (int i = 0; i < 6; i++) V[i] = alpha * (i < 3 ? 1.0 : 0.0) + (s[i] / ns) / sqrt(2.0);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 6; i++) V[i] = (i < 3 ? 1.0 / sqrt(3.0) : 0.0);
+                    }
+                    // D = De − (De·Nu)(De·V)ᵀ/(H + V·De·Nu) with Nu = V/|V| (j2 != 0) or Nu = V (j2 == 0, |V| = 1)
+                    const double nv = am_norm(V);
+                    double VD[6];
+                    am_De_mul(mp.E, mp.nu, V, VD);
+                    double vdv = 0.0;
+#pragma unroll
+                    for (int i = 0; i < 6; i++) vdv += VD[i] * V[i];
+                    const double den = nv * (H + vdv / nv);
+                    const double sc = 1.0 / sqrt(den);
+#pragma unroll
+                    for (int i = 0; i < 6; i++) wv[i] = VD[i] * sc;
+                    any = 1;
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < 6; c++) w[(int64_t)c * nip_total + ip] = wv[c];
+        }
+        pflag[e] = (uint8_t)any;
+    }
+}
+
+__global__ void k_count_flags(int64_t n, int nip, const uint8_t *__restrict__ f, unsigned long long *out) {
+    unsigned long long c = 0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) c += f[i] ? nip : 0;
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);   // integer count: order-independent
+}
+
+template <int NN, int ND, int NIP, int TA>
+int ebe_configure(amaru_model *m) {
+    int occ0 = 0, occ1 = 0;
+    const size_t s0 = EbeLayout<NN, ND, NIP, TA, false>::bytes, s1 = EbeLayout<NN, ND, NIP, TA, true>::bytes;
+    CUDA_CHECK(cudaFuncSetAttribute(k_ebe_apply<NN, ND, NIP, TA, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s0));
+    CUDA_CHECK(cudaFuncSetAttribute(k_ebe_apply<NN, ND, NIP, TA, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s1));
+    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ0, k_ebe_apply<NN, ND, NIP, TA, false>, EBE_NT, s0));
+    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ1, k_ebe_apply<NN, ND, NIP, TA, true>, EBE_NT, s1));
+    return m->nsm * std::max(1, std::min(std::min(occ0, occ1), 8));
+}
+
+Ebe *ebe_of(amaru_model *m) { return static_cast<Ebe *>(m->ebe); }
+
+}  // namespace
+
+// geometry planes + tangent planes; called from create_impl after the batches are on the device
+void amaru_ebe_setup(amaru_model *m) {
+    const char *op = getenv("AMARU_OPERATOR");
+    m->op_ebe = !(op && std::strcmp(op, "csr") == 0);
+    Ebe *E = new Ebe();
+    m->ebe = E;
+    E->b.resize(m->batches.size());
+    std::vector<double> dog((size_t)m->nmats * 3);
+    {
+        std::vector<double> par((size_t)m->nmats * AMARU_MAT_NPARAMS);
+        CUDA_CHECK(cudaMemcpy(par.data(), m->d_mat_par, par.size() * sizeof(double), cudaMemcpyDeviceToHost));
+        for (int i = 0; i < m->nmats; i++) {
+            const double Em = par[(size_t)i * AMARU_MAT_NPARAMS], nu = par[(size_t)i * AMARU_MAT_NPARAMS + 1];
+            const double c = Em / ((1.0 + nu) * (1.0 - 2.0 * nu));
+            dog[3 * i] = c * (1.0 - nu);
+            dog[3 * i + 1] = c * nu;
+            dog[3 * i + 2] = c * (1.0 - 2.0 * nu);
+        }
+    }
+    CUDA_CHECK(cudaMalloc(&E->d_dog, dog.size() * sizeof(double)));
+    CUDA_CHECK(cudaMemcpy(E->d_dog, dog.data(), dog.size() * sizeof(double), cudaMemcpyHostToDevice));
+    CUDA_CHECK(cudaMalloc(&E->d_w, std::max<size_t>((size_t)6 * m->nip_total, 1) * sizeof(double)));
+    CUDA_CHECK(cudaMemsetAsync(E->d_w, 0, std::max<size_t>((size_t)6 * m->nip_total, 1) * sizeof(double), m->stream));
+    CUDA_CHECK(cudaMalloc(&E->d_nplastic, sizeof(int64_t)));
+    for (size_t i = 0; i < m->batches.size(); i++) {
+        Batch &b = m->batches[i];
+        EbeBatch &eb = E->b[i];
+        const int64_t nipb = b.nelem * b.nip;
+        const int np = b.nd * b.nd + 1;
+        CUDA_CHECK(cudaMalloc(&eb.d_geo, std::max<size_t>((size_t)np * nipb, 1) * sizeof(double)));
+        CUDA_CHECK(cudaMalloc(&eb.d_pflag, std::max<size_t>((size_t)b.nelem, 1)));
+        CUDA_CHECK(cudaMemsetAsync(eb.d_pflag, 0, std::max<size_t>((size_t)b.nelem, 1), m->stream));
+        if (nipb == 0) continue;
+        const int g = (int)std::min<int64_t>((nipb + 127) / 128, (int64_t)m->nsm * 16);
+#define GEO(NN, ND, NIP) k_ebe_geometry<NN, ND, NIP><<<g, 128, 0, m->stream>>>(b.nelem, b.d_conn, m->d_coords, b.d_dNdR, b.d_w, m->th, eb.d_geo, nipb)
+        switch (b.shape) {
+        case AMARU_SHAPE_QUAD4: GEO(4, 2, 4); eb.grid = ebe_configure<4, 2, 4, 2>(m); break;
+        case AMARU_SHAPE_QUAD8: GEO(8, 2, 4); eb.grid = ebe_configure<8, 2, 4, 4>(m); break;
+        case AMARU_SHAPE_HEX8: GEO(8, 3, 8); eb.grid = ebe_configure<8, 3, 8, 2>(m); break;
+        case AMARU_SHAPE_HEX20: GEO(20, 3, 8); eb.grid = ebe_configure<20, 3, 8, 5>(m); break;
+        case AMARU_SHAPE_TET10: GEO(10, 3, 4); eb.grid = ebe_configure<10, 3, 4, 5>(m); break;
+        default: throw AmaruError{AMARU_ERR_UNSUPPORTED, "ebe: unsupported shape"};
+        }
+#undef GEO
+        m->launches++;
+        CUDA_CHECK(cudaGetLastError());
+    }
+}
+
+void amaru_ebe_destroy(amaru_model *m) {
+    Ebe *E = ebe_of(m);
+    if (!E) return;
+    for (EbeBatch &eb : E->b) {
+        cudaFree(eb.d_geo);
+        cudaFree(eb.d_pflag);
+        cudaFree(eb.d_eown);
+    }
+    cudaFree(E->d_w);
+    cudaFree(E->d_dog);
+    cudaFree(E->d_nplastic);
+    delete E;
+    m->ebe = nullptr;
+}
+
+// element ownership flags of a partitioned handle (abi.cu derives them from the halo lists): batch-local, colour-sorted
+void amaru_ebe_set_owned(amaru_model *m, int batch, const uint8_t *h_owned_sorted) {
+    Ebe *E = ebe_of(m);
+    Batch &b = m->batches[(size_t)batch];
+    EbeBatch &eb = E->b[(size_t)batch];
+    if (!eb.d_eown) CUDA_CHECK(cudaMalloc(&eb.d_eown, std::max<size_t>((size_t)b.nelem, 1)));
+    CUDA_CHECK(cudaMemcpy(eb.d_eown, h_owned_sorted, (size_t)b.nelem, cudaMemcpyHostToDevice));
+}
+
+// w planes from the current IP state (called by amaru_assemble_K: the operator then equals the assembled tangent)
+void amaru_ebe_refresh(amaru_model *m) {
+    Ebe *E = ebe_of(m);
+    if (!E) return;
+    CUDA_CHECK(cudaMemsetAsync(E->d_nplastic, 0, sizeof(int64_t), m->stream));
+    for (size_t i = 0; i < m->batches.size(); i++) {
+        Batch &b = m->batches[i];
+        if (b.nelem == 0) continue;
+        const int g = (int)std::min<int64_t>((b.nelem + 127) / 128, (int64_t)m->nsm * 16);
+        k_ebe_tangent<<<g, 128, 0, m->stream>>>(b.nip, b.nelem, b.ip_off, m->nip_total, b.d_emat, m->d_mat_kind, m->d_mat_par,
+                                                m->d_state, E->d_w, E->b[i].d_pflag);
+        k_count_flags<<<g, 128, 0, m->stream>>>(b.nelem, b.nip, E->b[i].d_pflag, reinterpret_cast<unsigned long long *>(E->d_nplastic));
+        m->launches += 2;
+    }
+    CUDA_CHECK(cudaGetLastError());
+    CUDA_CHECK(cudaMemcpyAsync(&E->nplastic_ip, E->d_nplastic, sizeof(int64_t), cudaMemcpyDeviceToHost, m->stream));
+}
+
+// y = (sysA·K + sysB·M) x on the owned rows (+ p·Ap and CG scalar finalisation when dot != 0); x needs valid ghost entries
+void amaru_ebe_apply(amaru_model *m, const double *x, double *y, int mask, int dot, int check_done, int finalize) {
+    Ebe *E = ebe_of(m);
+    AMARU_REQUIRE(E != nullptr, AMARU_ERR_ARG, "ebe: operator not set up");
+    const bool mass = m->sysB != 0.0;
+    CUDA_CHECK(cudaMemsetAsync(y, 0, (size_t)m->nowned * m->nd * sizeof(double), m->stream));
+    // number of non-empty colour launches, to flag the last one
+    int nl = 0, il = 0;
+    for (Batch &b : m->batches)
+        for (size_t c = 0; c + 1 < b.color_off.size(); c++) nl += b.color_off[c + 1] > b.color_off[c];
+    EbeArgs a;
+    a.dog = E->d_dog; a.w = E->d_w; a.nip_total = m->nip_total; a.sa = m->sysA; a.sb = m->sysB;
+    a.x = x; a.y = y; a.fixed = m->d_fixed; a.mask = mask; a.nowned = m->nowned;
+    a.partial = m->d_partial; a.scal = m->d_scal; a.dot = dot; a.finalize = finalize; a.check_done = check_done;
+    a.first = 1;
+    for (size_t i = 0; i < m->batches.size(); i++) {
+        Batch &b = m->batches[i];
+        EbeBatch &eb = E->b[i];
+        AMARU_REQUIRE(!mass || b.d_rho != nullptr, AMARU_ERR_ARG, "ebe: mass term without densities (call amaru_assemble_M)");
+        a.conn = b.d_conn; a.emat = b.d_emat; a.eown = eb.d_eown; a.pflag = eb.d_pflag; a.geo = eb.d_geo;
+        a.nipb = b.nelem * b.nip; a.ip_off = b.ip_off; a.dNdR = b.d_dNdR; a.Nf = b.d_N; a.rho = b.d_rho;
+        for (size_t c = 0; c + 1 < b.color_off.size(); c++) {
+            const int64_t n = b.color_off[c + 1] - b.color_off[c];
+            if (n <= 0) continue;
+            il++;
+            a.e_begin = b.color_off[c];
+            a.e_end = b.color_off[c + 1];
+            a.last = il == nl;
+            const int epb = EBE_NT / b.nip;
+            const int grid = (int)std::min<int64_t>((n + epb - 1) / epb, eb.grid);
+#define APPLY(NN, ND, NIP, TA)                                                                                         \
+    do {                                                                                                               \
+        if (mass) k_ebe_apply<NN, ND, NIP, TA, true><<<grid, EBE_NT, EbeLayout<NN, ND, NIP, TA, true>::bytes, m->stream>>>(a);   \
+        else k_ebe_apply<NN, ND, NIP, TA, false><<<grid, EBE_NT, EbeLayout<NN, ND, NIP, TA, false>::bytes, m->stream>>>(a);      \
+    } while (0)
+            switch (b.shape) {
+            case AMARU_SHAPE_QUAD4: APPLY(4, 2, 4, 2); break;
+            case AMARU_SHAPE_QUAD8: APPLY(8, 2, 4, 4); break;
+            case AMARU_SHAPE_HEX8: APPLY(8, 3, 8, 2); break;
+            case AMARU_SHAPE_HEX20: APPLY(20, 3, 8, 5); break;
+            case AMARU_SHAPE_TET10: APPLY(10, 3, 4, 5); break;
+            default: throw AmaruError{AMARU_ERR_UNSUPPORTED, "ebe: unsupported shape"};
+            }
+#undef APPLY
+            m->launches++;
+            a.first = 0;
+        }
+    }
+    CUDA_CHECK(cudaGetLastError());
+}
+
+// algorithmic bytes of one application
+int64_t amaru_ebe_bytes(const amaru_model *m) {
+    const Ebe *E = static_cast<const Ebe *>(m->ebe);
+    int64_t bytes = 0;
+    for (const Batch &b : m->batches) bytes += (int64_t)8 * (b.nd * b.nd + 1) * b.nelem * b.nip + (int64_t)4 * b.nn * b.nelem + 5 * b.nelem;
+    bytes += 48 * (E ? E->nplastic_ip : 0);
+    bytes += 16 * m->nowned * m->nd;
+    return bytes;
+}
+
+const char *amaru_ebe_kernel(const amaru_model *m) {
+    if (m->batches.empty()) return "k_ebe_apply";
+    switch (m->batches[0].shape) {
+    case AMARU_SHAPE_QUAD4: return "k_ebe_apply<4,2,4,2>";
+    case AMARU_SHAPE_QUAD8: return "k_ebe_apply<8,2,4,4>";
+    case AMARU_SHAPE_HEX8: return "k_ebe_apply<8,3,8,2>";
+    case AMARU_SHAPE_HEX20: return "k_ebe_apply<20,3,8,5>";
+    case AMARU_SHAPE_TET10: return "k_ebe_apply<10,3,4,5>";
+    }
+    return "k_ebe_apply";
+}

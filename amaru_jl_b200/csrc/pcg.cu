@@ -289,6 +289,12 @@ void amaru_spmv(amaru_model *m, const double *A, const double *x, double *y, int
     amaru_spmv_launch(m, A, x, y, mask_mode, 0, 0, 0);
 }
 
+// y = A x with the system matrix of the solve (unmasked, no dot): matrix-free or from the assembled block-CSR values
+static void amaru_system_product(amaru_model *m, const double *x, double *y) {
+    if (m->op_ebe) amaru_ebe_apply(m, x, y, 0, 0, 0, 0);
+    else amaru_spmv(m, m->d_A, x, y, 0);
+}
+
 static void spmv_dot(amaru_model *m, const double *A, const double *x, double *y, int finalize) {
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (m->profiling) {
@@ -296,13 +302,34 @@ static void spmv_dot(amaru_model *m, const double *A, const double *x, double *y
         CUDA_CHECK(cudaEventCreate(&e1));
         CUDA_CHECK(cudaEventRecord(e0, m->stream));
     }
-    if (m->use_sym && A == m->d_A) amaru_spmv_sym_launch(m, x, y, 1, 1, 1, finalize);   // half the bytes (spmv.cu)
+    if (m->op_ebe && A == m->d_A) amaru_ebe_apply(m, x, y, 1, 1, 1, finalize);               // matrix-free (ebe.cu)
+    else if (m->use_sym && A == m->d_A) amaru_spmv_sym_launch(m, x, y, 1, 1, 1, finalize);   // half the bytes (spmv.cu)
     else amaru_spmv_launch(m, A, x, y, 1, 1, 1, finalize);
     if (m->profiling) {
         CUDA_CHECK(cudaEventRecord(e1, m->stream));
         m->ev_pool.push_back(e0);
         m->ev_pool.push_back(e1);
     }
+}
+
+// test / measurement hook: q = A p with the handle's CG operator; masked != 0 also runs the fused p.Ap (returned)
+double amaru_operator_product(amaru_model *m, int masked) {
+    amaru_spmv_sym_refresh(m);
+    CUDA_CHECK(cudaMemsetAsync(m->d_scal, 0, sizeof(CgScalars), m->stream));
+    if (m->nranks > 1) amaru_halo_exchange(m, m->d_p);
+    if (masked) {
+        const bool prof = m->profiling;
+        m->profiling = false;
+        spmv_dot(m, m->d_A, m->d_p, m->d_q, 0);
+        m->profiling = prof;
+        if (m->nranks > 1) amaru_allreduce_sum(m, m->d_scal->acc, 1);
+    } else {
+        amaru_system_product(m, m->d_p, m->d_q);
+    }
+    CgScalars *h = reinterpret_cast<CgScalars *>(m->h_pinned);
+    CUDA_CHECK(cudaMemcpyAsync(h, m->d_scal, sizeof(CgScalars), cudaMemcpyDeviceToHost, m->stream));
+    CUDA_CHECK(cudaStreamSynchronize(m->stream));
+    return m->nranks > 1 ? h->acc[0] : h->pq;
 }
 
 static void build_preconditioner(amaru_model *m, int precond) {
@@ -329,7 +356,7 @@ static void cg_loop(amaru_model *m, double rtol, int maxit, SolveInfo &info) {
     CgScalars *h = reinterpret_cast<CgScalars *>(m->h_pinned);
     // t = A*[0;U2] (the caller zeroed the free entries of d_x), r = b - t on the free dofs
     if (multi) amaru_halo_exchange(m, m->d_x);
-    amaru_spmv(m, m->d_A, m->d_x, m->d_q, 0);
+    amaru_system_product(m, m->d_x, m->d_q);
     k_cg_init<BS, BJ><<<gn, ROW_THREADS, 0, m->stream>>>(m->nowned, m->d_b, m->d_q, m->d_fixed, m->d_Minv, m->d_x, m->d_r,
                                                           m->d_z, m->d_p, m->d_partial, m->d_scal, rtol * rtol, maxit, fin);
     m->launches++;
@@ -346,11 +373,13 @@ static void cg_loop(amaru_model *m, double rtol, int maxit, SolveInfo &info) {
     cudaGraphExec_t gexec = nullptr;
     const bool use_graph = !multi && !m->profiling && m->cg_graph;
     bool finished = false;
+    int64_t batch_launches = 0;
     while (!finished) {
         if (use_graph && gexec) {
             CUDA_CHECK(cudaGraphLaunch(gexec, m->stream));
-            m->launches += 3 * CG_BATCH;
+            m->launches += batch_launches;
         } else {
+        const int64_t l0 = m->launches;
         if (use_graph) CUDA_CHECK(cudaStreamBeginCapture(m->stream, cudaStreamCaptureModeThreadLocal));
         for (int it = 0; it < CG_BATCH; it++) {
             if (multi) amaru_halo_exchange(m, m->d_p);
@@ -375,6 +404,7 @@ static void cg_loop(amaru_model *m, double rtol, int maxit, SolveInfo &info) {
             CUDA_CHECK(cudaGraphInstantiate(&gexec, graph, 0));
             CUDA_CHECK(cudaGraphDestroy(graph));
             CUDA_CHECK(cudaGraphLaunch(gexec, m->stream));
+            batch_launches = m->launches - l0;
         }
         }
         CUDA_CHECK(cudaGetLastError());
@@ -426,7 +456,7 @@ void amaru_pcg_solve(amaru_model *m, double rtol, int maxit, int precond, SolveI
     }
     // reactions: q = A*x over all rows (solver.jl:32,57: F2 = K22*U2 + K21*U1)
     if (m->nranks > 1) amaru_halo_exchange(m, m->d_x);
-    amaru_spmv(m, m->d_A, m->d_x, m->d_q, 0);
+    amaru_system_product(m, m->d_x, m->d_q);
     // max |U1| (solver.jl:68-71)
     k_reset_flags<<<1, 1, 0, m->stream>>>(m->d_scal);
     k_maxabs_nan<<<blocks_for(m, nloc, 256), 256, 0, m->stream>>>(nloc, m->d_x, m->d_fixed, 1, m->d_scal);

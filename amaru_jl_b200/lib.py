@@ -81,6 +81,8 @@ SYMBOLS = {
                                                 C.c_char_p, C.c_int]),
     "amaru_set_device_vectors": (C.c_int, [_vp, _dp, _dp, C.c_char_p, C.c_int]),
     "amaru_time_kernel": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _dp, C.c_char_p, C.c_int]),
+    "amaru_set_operator": (C.c_int, [_vp, C.c_int]),
+    "amaru_operator_apply": (C.c_int, [_vp, _dp, _dp, C.c_int, _dp, C.c_char_p, C.c_int]),
     "amaru_set_profiling": (C.c_int, [_vp, C.c_int]),
     "amaru_get_profile": (C.c_int, [_vp, _dp, _i64p]),
     "amaru_spmv_bytes": (C.c_int64, [_vp]),
@@ -357,6 +359,20 @@ class DeviceModel:
         self._check(self.lib.amaru_time_kernel(self.h, int(kind), int(precond), int(reps), C.byref(t), self._msg,
                                                len(self._msg)))
         return t.value
+
+    def set_operator(self, kind):
+        """CG operator of this handle: "ebe" (matrix-free, default) or "csr" (SpMV on the assembled block-CSR values)."""
+        k = {"csr": 0, "ebe": 1}[kind] if isinstance(kind, str) else int(kind)
+        self._check(self.lib.amaru_set_operator(self.h, k))
+
+    def operator_apply(self, x, masked=False):
+        """(A x, x.Ax) with the CG operator of this handle (``set_operator``); eq_id ordering."""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        y = np.empty(self.ndofs)
+        pq = C.c_double(0)
+        self._check(self.lib.amaru_operator_apply(self.h, _d(x), _d(y), 1 if masked else 0, C.byref(pq), self._msg,
+                                                  len(self._msg)))
+        return y, pq.value
 
     def set_profiling(self, on=True):
         self.lib.amaru_set_profiling(self.h, 1 if on else 0)

@@ -67,6 +67,13 @@ extern "C" {
 #define AMARU_PRECOND_JACOBI 0
 #define AMARU_PRECOND_BLOCK_JACOBI 1 /* nd x nd node blocks */
 
+/* operator the PCG applies each iteration in place of K11*p (solver.jl:42-43 factorises K11 instead):
+ *   EBE (default): matrix-free, re-integrated per element from the per-IP tangent data that amaru_assemble_K refreshes;
+ *   CSR          : SpMV on the assembled block-CSR values.  Both use the same assembled K for the preconditioner, for
+ *   amaru_get_csr and for amaru_matvec.  AMARU_OPERATOR=csr|ebe in the environment sets the default of new handles. */
+#define AMARU_OPERATOR_CSR 0
+#define AMARU_OPERATOR_EBE 1
+
 typedef struct amaru_model amaru_model; /* opaque */
 
 /* Library / device probe.  Returns the number of visible CUDA devices (0 = none), <0 on error. */
@@ -256,6 +263,12 @@ int amaru_set_device_vectors(amaru_model *m, const double *U, const double *F, c
 /* time `reps` launches of one kernel class on the model's stream (CUDA events); kind: 0 SpMV, 1 assemble,
  * 2 update_state, 3 fused CG vector update, 4 p-update. Returns average ms per launch. */
 int amaru_time_kernel(amaru_model *m, int kind, int precond, int reps, double *avg_ms, char *msg, int msglen);
+/* AMARU_OPERATOR_CSR | AMARU_OPERATOR_EBE for the following amaru_solve calls of this handle */
+int amaru_set_operator(amaru_model *m, int kind);
+/* y = A x with the operator the PCG of this handle applies (EBE or CSR) and the current system matrix a*K + b*M, in
+ * eq_id ordering over all ndofs.  masked != 0: rows of prescribed dofs are zeroed, as inside the CG loop, and *pAp
+ * receives the fused x.Ax (equal to the masked dot when x vanishes on the prescribed dofs).  For parity tests. */
+int amaru_operator_apply(amaru_model *m, const double *x, double *y, int masked, double *pAp, char *msg, int msglen);
 /* When on, amaru_solve brackets every CG SpMV launch with CUDA events on the model's stream; amaru_get_profile
  * returns the summed duration (ms) and the number of SpMV launches since profiling was switched on. */
 int amaru_set_profiling(amaru_model *m, int on);
