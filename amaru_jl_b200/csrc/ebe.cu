@@ -30,12 +30,18 @@
 
 namespace {
 
-constexpr int EBE_NT = 256;
+constexpr int EBE_NT = 128;   // threads per CTA: 16 HEX20 / 32 TET10 elements per group
+
+
+constexpr uint32_t EC_NODE = 0x0fffffffu;   // econn entry: node | prescribed-dof mask << 28 | ghost << 31
+constexpr int EI_PLASTIC = 1 << 30;          // einfo entry: material | plastic << 30 | not-owned << 31
+constexpr int EI_MAT = (1 << 30) - 1;
+constexpr int EBE_SMATS = 32;                // material moduli staged in shared memory up to this many materials
 
 struct EbeBatch {          // per element batch, colour-sorted element order (same order as the IP state planes)
     double *d_geo = nullptr;      // [(nd*nd+1)][nipb]: J⁻¹ row-major planes, then coef
-    uint8_t *d_pflag = nullptr;   // [nelem] 1 = some IP of the element has w != 0
-    uint8_t *d_eown = nullptr;    // [nelem] 1 = this rank owns the element (counts in p·Ap); nullptr = all owned
+    int32_t *d_econn = nullptr;   // [nelem*nn] node | prescribed-dof mask << 28 | ghost << 31
+    int32_t *d_einfo = nullptr;   // [nelem] material | (some IP has w != 0) << 30 | (element owned by another rank) << 31
     int grid = 1;
 };
 
@@ -43,16 +49,15 @@ struct Ebe {
     std::vector<EbeBatch> b;
     double *d_w = nullptr;        // [6][nip_total]
     double *d_dog = nullptr;      // [nmats][3]: c(1-ν), cν, c(1-2ν)
-    int64_t *d_nplastic = nullptr;   // device counter of flagged elements (for the byte count)
+    int64_t *d_nplastic = nullptr;   // device counter of IPs in flagged elements (for the byte count)
     int64_t nplastic_ip = 0;
 };
 
 struct EbeArgs {
-    const int32_t *conn;
-    const int32_t *emat;
-    const uint8_t *eown;
-    const uint8_t *pflag;
+    const int32_t *econn;
+    const int32_t *einfo;
     const double *dog;
+    int nmats;
     const double *geo;
     int64_t nipb;
     const double *w;
@@ -63,74 +68,144 @@ struct EbeArgs {
     double sa, sb;
     const double *x;
     double *y;
-    const uint8_t *fixed;
     int mask;
-    int64_t nowned;
     int64_t e_begin, e_end;
     double *partial;
     CgScalars *scal;
     int dot, first, last, finalize, check_done;
 };
 
-template <int NN, int ND, int NIP, int TA, bool MASS>
+template <int NN, int ND, int NIP, int TA, bool MASS, int NT>
 struct EbeLayout {
-    static constexpr int EPB = EBE_NT / NIP;
+    static constexpr int EPB = NT / NIP;                     // elements per group
+    static constexpr int NP = ND * ND + 1;                   // geometry planes
     static constexpr int QS = (ND * NN) | 1;                 // stride of one integration point in the dN table (odd)
     static constexpr int US = (NN * ND) | 1;                 // stride of one element in the x stage (odd)
     static constexpr int SQ = ND * ND + (MASS ? ND : 0);     // S (+ mass vector) of one integration point
     static constexpr int ES = (NIP * SQ) | 1;                // stride of one element in the S stage (odd)
-    static constexpr int NTH3 = NN / TA;                     // phase-3 threads per element
-    static constexpr size_t doubles = (size_t)NIP * QS + (MASS ? NIP * NN : 0) + (size_t)EPB * US + (size_t)EPB * ES;
-    static constexpr size_t bytes = doubles * 8 + (size_t)EPB * NN * 4;
+    static constexpr int NTH3 = NN / TA;                     // phase-3 node groups per element (x 2 halves of the IPs)
+    static constexpr int NLD = (EPB * NN + NT - 1) / NT;     // element-node ids per thread and group
+    static constexpr int NGC = (NP * (NT / 2) + NT - 1) / NT;   // 16-byte geometry chunks per thread and group
+    static constexpr size_t doubles = (size_t)NIP * QS + (MASS ? NIP * NN : 0) + 3 * EBE_SMATS + (size_t)2 * EPB * US +
+                                      (size_t)2 * NP * NT + (size_t)EPB * ES;
+    static constexpr size_t bytes = doubles * 8 + (size_t)2 * EPB * NN * 4;
     static_assert(NN % TA == 0, "TA must divide NN");
-    static_assert(EPB * NTH3 <= EBE_NT, "phase 3 needs more threads than the CTA has");
+    static_assert(EPB * NTH3 * 2 == NT, "phase 3 must use every thread: (NN/TA)*2 == NIP");
+    static_assert(NIP % 2 == 0, "phase 3 splits the integration points in two halves");
 };
 
-template <int NN, int ND, int NIP, int TA, bool MASS>
-__global__ void __launch_bounds__(EBE_NT) k_ebe_apply(EbeArgs p) {
+// Group pipeline of one CTA (2 barriers per group, nothing but shared memory and registers on the critical path):
+//   (B) x and the geometry planes of group g have landed in stage `buf` (cp.async issued one group earlier) and everybody
+//       left phase 3 of g-1 -> start the cp.async copies of group g+1 into the other stage; the node ids of group g+2 and
+//       the element record of group g+1 go to registers
+//   phase 2 (g): thread = (element, integration point)           -> S stage
+//   (C)
+//   phase 3 (g): thread = (element, TA nodes, half of the IPs); the y entries are loaded into the accumulators up front,
+//       the two halves are combined with one xor-shuffle and each lane stores its share of the TA nodes.
+template <int NN, int ND, int NIP, int TA, bool MASS, int NT>
+__global__ void __launch_bounds__(NT) k_ebe_apply(EbeArgs p) {
     if (p.check_done && p.scal->done) return;
-    using L = EbeLayout<NN, ND, NIP, TA, MASS>;
-    constexpr int EPB = L::EPB, QS = L::QS, US = L::US, SQ = L::SQ, ES = L::ES, NTH3 = L::NTH3;
+    using L = EbeLayout<NN, ND, NIP, TA, MASS, NT>;
+    constexpr int EPB = L::EPB, NP = L::NP, QS = L::QS, US = L::US, SQ = L::SQ, ES = L::ES, NTH3 = L::NTH3, NLD = L::NLD,
+                  NGC = L::NGC;
     extern __shared__ __align__(16) double esm[];
     double *sdN = esm;                                   // [NIP][QS]: dN[q][k][a] at q*QS + k*NN + a
     double *sNf = sdN + NIP * QS;                        // [NIP][NN] (mass only)
-    double *sU = sNf + (MASS ? NIP * NN : 0);            // [EPB][US]: x of element-node (a, i) at e*US + a*ND + i
-    double *sS = sU + EPB * US;                          // [EPB][ES]: S[q][k][i] at e*ES + q*SQ + k*ND + i
-    int32_t *sNode = reinterpret_cast<int32_t *>(sS + EPB * ES);   // [EPB][NN]
+    double *sDog = sNf + (MASS ? NIP * NN : 0);          // [EBE_SMATS][3]
+    double *sU = sDog + 3 * EBE_SMATS;                   // [2][EPB][US]: x of element-node (a, i) at e*US + a*ND + i
+    double *sGeo = sU + 2 * EPB * US;                    // [2][NP][NT]: plane k of IP t at k*NT + t
+    double *sS = sGeo + 2 * NP * NT;                     // [EPB][ES]: S[q][k][i] at e*ES + q*SQ + k*ND + i
+    int32_t *sNode = reinterpret_cast<int32_t *>(sS + EPB * ES);   // [2][EPB][NN] (econn entries)
     const int tid = threadIdx.x;
-    for (int i = tid; i < NIP * NN * ND; i += EBE_NT) {   // global table is [q][a][k]
+    for (int i = tid; i < NIP * NN * ND; i += NT) {      // global table is [q][a][k]
         const int q = i / (NN * ND), r = i - q * NN * ND, a = r / ND, k = r - a * ND;
         sdN[q * QS + k * NN + a] = p.dNdR[i];
     }
     if (MASS)
-        for (int i = tid; i < NIP * NN; i += EBE_NT) sNf[i] = p.Nf[i];
+        for (int i = tid; i < NIP * NN; i += NT) sNf[i] = p.Nf[i];
+    const bool smats = p.nmats <= EBE_SMATS;
+    if (smats)
+        for (int i = tid; i < 3 * p.nmats; i += NT) sDog[i] = p.dog[i];
     double dsum[1] = {0.0};
     const int64_t ngroups = (p.e_end - p.e_begin + EPB - 1) / EPB;
-    for (int64_t g = blockIdx.x; g < ngroups; g += gridDim.x) {
+    const int64_t stride = gridDim.x;
+    int32_t nreg[NLD];
+    auto load_conn = [&](int64_t g) {                    // econn entries of group g -> registers (0 nodes past the end)
+        const int64_t ge = p.e_begin + g * EPB;          // first element of the group
+#pragma unroll
+        for (int j = 0; j < NLD; j++) {
+            const int i = tid + j * NT;
+            nreg[j] = (g < ngroups && i < EPB * NN && ge * NN + i < p.e_end * NN) ? p.econn[ge * NN + i] : -1;
+        }
+    };
+    auto load_einfo = [&](int64_t g) -> int {            // record of the element this thread integrates in phase 2
+        const int64_t e = p.e_begin + g * EPB + tid / NIP;
+        return (g < ngroups && e < p.e_end) ? p.einfo[e] : 0;
+    };
+    auto issue_copies = [&](int64_t g, int buf) {        // x of the nodes in nreg and the geometry planes of group g -> stage buf
+#pragma unroll
+        for (int j = 0; j < NLD; j++) {
+            const int i = tid + j * NT;
+            const int32_t ent = nreg[j];
+            if (ent != -1) {
+                sNode[buf * EPB * NN + i] = ent;
+                const int e = i / NN, a = i - e * NN;
+                const uint32_t dst = (uint32_t)__cvta_generic_to_shared(sU + (buf * EPB + e) * US + a * ND);
+                const double *src = p.x + (int64_t)((uint32_t)ent & EC_NODE) * ND;
+#pragma unroll
+                for (int d = 0; d < ND; d++)
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + d * 8u), "l"(src + d) : "memory");
+            }
+        }
+        if (g < ngroups) {
+            const int64_t e0 = p.e_begin + g * EPB;
+            const int nv = (int)min((int64_t)EPB, p.e_end - e0) * NIP;   // valid doubles per plane (even)
+            const double *gsrc = p.geo + e0 * NIP;
+            const uint32_t gdst = (uint32_t)__cvta_generic_to_shared(sGeo + buf * NP * NT);
+#pragma unroll
+            for (int j = 0; j < NGC; j++) {
+                const int c = tid + j * NT;
+                const int k = c / (NT / 2), o = (c - k * (NT / 2)) * 2;
+                if (k < NP && o < nv)
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(gdst + (uint32_t)(k * NT + o) * 8u),
+                                 "l"(gsrc + (int64_t)k * p.nipb + o) : "memory");
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    load_conn(blockIdx.x);
+    int ei = load_einfo(blockIdx.x);
+    issue_copies(blockIdx.x, 0);
+    load_conn(blockIdx.x + stride);
+    int buf = 0;
+    for (int64_t g = blockIdx.x; g < ngroups; g += stride, buf ^= 1) {
         const int64_t e0 = p.e_begin + g * EPB;
         const int ne = (int)min((int64_t)EPB, p.e_end - e0);
-        __syncthreads();   // previous group's phase 3 is done with sS / sNode (and the tables are staged)
-        // ---- phase 1: x of the group's element nodes
-        for (int i = tid; i < ne * NN; i += EBE_NT) {
-            const int e = i / NN, a = i - e * NN;
-            const int32_t node = p.conn[e0 * NN + i];
-            sNode[i] = node;
-#pragma unroll
-            for (int d = 0; d < ND; d++) sU[e * US + a * ND + d] = p.x[(int64_t)node * ND + d];
-        }
-        __syncthreads();
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();                                 // (B)
+        issue_copies(g + stride, buf ^ 1);
+        load_conn(g + 2 * stride);
+        const int ei_next = load_einfo(g + stride);
         // ---- phase 2: one thread per (element, integration point)
         {
             const int e = tid / NIP, q = tid - e * NIP;
             if (e < ne) {
-                const int64_t ipb = (e0 + e) * NIP + q;              // position inside the batch's planes
+                const double *gp = sGeo + buf * NP * NT + tid;
+                const bool plastic = (ei & EI_PLASTIC) != 0;
+                double w[6];
+                if (plastic) {
+                    const int64_t ip = p.ip_off + (e0 + e) * NIP + q;
+#pragma unroll
+                    for (int c = 0; c < 6; c++) w[c] = p.w[(int64_t)c * p.nip_total + ip];
+                }
+                const double *dg = (smats ? sDog : p.dog) + 3 * (ei & EI_MAT);
                 double G[ND * ND];
 #pragma unroll
                 for (int k = 0; k < ND * ND; k++) G[k] = 0.0;
                 double ub[ND];
 #pragma unroll
                 for (int d = 0; d < ND; d++) ub[d] = 0.0;
-                const double *U = sU + e * US, *dn = sdN + q * QS;
+                const double *U = sU + (buf * EPB + e) * US, *dn = sdN + q * QS;
 #pragma unroll 4
                 for (int a = 0; a < NN; a++) {
                     double u[ND], d_[ND];
@@ -150,8 +225,8 @@ __global__ void __launch_bounds__(EBE_NT) k_ebe_apply(EbeArgs p) {
                 }
                 double Ji[ND * ND];
 #pragma unroll
-                for (int k = 0; k < ND * ND; k++) Ji[k] = p.geo[(int64_t)k * p.nipb + ipb];
-                const double coef = p.geo[(int64_t)(ND * ND) * p.nipb + ipb];
+                for (int k = 0; k < ND * ND; k++) Ji[k] = gp[k * NT];
+                const double coef = gp[ND * ND * NT];
                 double H[ND * ND];
 #pragma unroll
                 for (int i = 0; i < ND; i++)
@@ -169,20 +244,15 @@ __global__ void __launch_bounds__(EBE_NT) k_ebe_apply(EbeArgs p) {
                 } else {
                     ep[0] = H[0]; ep[1] = H[3]; ep[2] = 0.0; ep[3] = 0.0; ep[4] = 0.0; ep[5] = (H[1] + H[2]) / AM_SR2;
                 }
-                const double *dg = p.dog + 3 * p.emat[e0 + e];
                 const double dd = dg[0], oo = dg[1], gg = dg[2];
                 sg[0] = dd * ep[0] + oo * ep[1] + oo * ep[2];
                 sg[1] = oo * ep[0] + dd * ep[1] + oo * ep[2];
                 sg[2] = oo * ep[0] + oo * ep[1] + dd * ep[2];
                 sg[3] = gg * ep[3]; sg[4] = gg * ep[4]; sg[5] = gg * ep[5];
-                if (p.pflag[e0 + e]) {
-                    const int64_t ip = p.ip_off + ipb;
-                    double w[6], t = 0.0;
+                if (plastic) {
+                    double t = 0.0;
 #pragma unroll
-                    for (int c = 0; c < 6; c++) {
-                        w[c] = p.w[(int64_t)c * p.nip_total + ip];
-                        t += w[c] * ep[c];
-                    }
+                    for (int c = 0; c < 6; c++) t += w[c] * ep[c];
 #pragma unroll
                     for (int c = 0; c < 6; c++) sg[c] -= w[c] * t;
                 }
@@ -216,62 +286,73 @@ __global__ void __launch_bounds__(EBE_NT) k_ebe_apply(EbeArgs p) {
                         en += cm * ub[i] * ub[i];
                     }
                 }
-                if (p.dot && (p.eown == nullptr || p.eown[e0 + e])) dsum[0] += en;
+                if (p.dot && ei >= 0) dsum[0] += en;     // bit 31 of the record: the element belongs to another rank
             }
         }
-        __syncthreads();
-        // ---- phase 3: one thread per (element, TA nodes): f_a = Σ_q Σ_k dN[q][k][a]·S[q][k][:] (+ N_a(q)·m(q))
-        if (tid < ne * NTH3) {
-            const int e = tid / NTH3, a0 = (tid - e * NTH3) * TA;
+        ei = ei_next;
+        __syncthreads();                                 // (C)
+        // ---- phase 3: thread = (element, TA nodes, half h of the integration points)
+        {
+            constexpr int TS = (TA + 1) / 2;             // lane h = 0 stores nodes [0, TS), lane h = 1 nodes [TS, TA)
+            const int e = tid / (2 * NTH3), r3 = tid - e * (2 * NTH3), a0 = (r3 >> 1) * TA, h = r3 & 1;
+            const bool active = e < ne;
             double f[TA][ND];
+            int64_t yk[TA];                              // first dof of the node this lane stores, or -1
+            uint32_t skip = 0;                           // bit t*ND+i: prescribed dof (masked product)
+#pragma unroll
+            for (int t = 0; t < TA; t++) {
+                const bool mine = active && ((t < TS) == (h == 0));
+                const uint32_t ent = mine ? (uint32_t)sNode[(buf * EPB + e) * NN + a0 + t] : 0x80000000u;
+                const bool st = !(ent >> 31);            // ghost rows belong to the neighbour rank
+                yk[t] = st ? (int64_t)(ent & EC_NODE) * ND : -1;
+                if (p.mask) skip |= ((ent >> 28) & 7u) << (t * ND);
+#pragma unroll
+                for (int i = 0; i < ND; i++) f[t][i] = st ? p.y[yk[t] + i] : 0.0;
+            }
+            if (active) {
+                const double *S = sS + e * ES;
+#pragma unroll 2
+                for (int qq = 0; qq < NIP / 2; qq++) {
+                    const int q = h * (NIP / 2) + qq;
+#pragma unroll
+                    for (int k = 0; k < ND; k++) {
+                        double s[ND], d_[TA];
+#pragma unroll
+                        for (int i = 0; i < ND; i++) s[i] = S[q * SQ + k * ND + i];
+#pragma unroll
+                        for (int t = 0; t < TA; t++) d_[t] = sdN[q * QS + k * NN + a0 + t];
+#pragma unroll
+                        for (int t = 0; t < TA; t++)
+#pragma unroll
+                            for (int i = 0; i < ND; i++) f[t][i] += d_[t] * s[i];
+                    }
+                    if (MASS) {
+                        double mv[ND];
+#pragma unroll
+                        for (int i = 0; i < ND; i++) mv[i] = S[q * SQ + ND * ND + i];
+#pragma unroll
+                        for (int t = 0; t < TA; t++) {
+                            const double n = sNf[q * NN + a0 + t];
+#pragma unroll
+                            for (int i = 0; i < ND; i++) f[t][i] += n * mv[i];
+                        }
+                    }
+                }
+            }
 #pragma unroll
             for (int t = 0; t < TA; t++)
 #pragma unroll
-                for (int i = 0; i < ND; i++) f[t][i] = 0.0;
-            const double *S = sS + e * ES;
-#pragma unroll 2
-            for (int q = 0; q < NIP; q++) {
-#pragma unroll
-                for (int k = 0; k < ND; k++) {
-                    double s[ND], d_[TA];
-#pragma unroll
-                    for (int i = 0; i < ND; i++) s[i] = S[q * SQ + k * ND + i];
-#pragma unroll
-                    for (int t = 0; t < TA; t++) d_[t] = sdN[q * QS + k * NN + a0 + t];
-#pragma unroll
-                    for (int t = 0; t < TA; t++)
-#pragma unroll
-                        for (int i = 0; i < ND; i++) f[t][i] += d_[t] * s[i];
+                for (int i = 0; i < ND; i++) {
+                    const double tot = f[t][i] + __shfl_xor_sync(0xffffffffu, f[t][i], 1);
+                    if (yk[t] >= 0 && !((skip >> (t * ND + i)) & 1u)) p.y[yk[t] + i] = tot;
                 }
-                if (MASS) {
-                    double mv[ND];
-#pragma unroll
-                    for (int i = 0; i < ND; i++) mv[i] = S[q * SQ + ND * ND + i];
-#pragma unroll
-                    for (int t = 0; t < TA; t++) {
-                        const double n = sNf[q * NN + a0 + t];
-#pragma unroll
-                        for (int i = 0; i < ND; i++) f[t][i] += n * mv[i];
-                    }
-                }
-            }
-#pragma unroll
-            for (int t = 0; t < TA; t++) {
-                const int64_t node = sNode[e * NN + a0 + t];
-                if (node < p.nowned) {   // ghost rows belong to the neighbour rank (it integrates the element too)
-#pragma unroll
-                    for (int i = 0; i < ND; i++) {
-                        const int64_t k = node * ND + i;
-                        if (!(p.mask && p.fixed[k])) p.y[k] += f[t][i];
-                    }
-                }
-            }
         }
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     if (p.dot) {
-        block_sum<1, EBE_NT>(dsum);
+        block_sum<1, NT>(dsum);
         if (publish_partials<1>(dsum, p.partial, &p.scal->counter[0])) {
-            sum_partials<1, EBE_NT>(dsum, p.partial);
+            sum_partials<1, NT>(dsum, p.partial);
             if (threadIdx.x == 0) {
                 const double acc = p.first ? dsum[0] : p.scal->pq + dsum[0];   // colours are summed in launch order
                 p.scal->pq = acc;
@@ -283,6 +364,22 @@ __global__ void __launch_bounds__(EBE_NT) k_ebe_apply(EbeArgs p) {
             }
         }
     }
+}
+
+// econn / einfo of a batch (once per handle)
+__global__ void k_ebe_econn(int64_t n, int nd, int64_t nowned, const int32_t *__restrict__ conn, const uint8_t *__restrict__ fixed,
+                            int32_t *econn) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int32_t node = conn[i];
+        uint32_t v = (uint32_t)node;
+        for (int d = 0; d < nd; d++) v |= (uint32_t)(fixed[(int64_t)node * nd + d] ? 1u : 0u) << (28 + d);
+        if (node >= nowned) v |= 1u << 31;
+        econn[i] = (int32_t)v;
+    }
+}
+__global__ void k_ebe_einfo(int64_t n, const int32_t *__restrict__ emat, const uint8_t *__restrict__ owned, int32_t *einfo) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        einfo[i] = (einfo[i] & EI_PLASTIC) | emat[i] | ((owned && !owned[i]) ? (int)0x80000000 : 0);
 }
 
 // J⁻¹ and coef = detJ·w·th of every integration point (once per handle: the geometry does not change)
@@ -310,7 +407,7 @@ __global__ void k_ebe_geometry(int64_t nelem, const int32_t *__restrict__ conn, 
 // w of every integration point from the current IP state (calcD of the three materials in rank-one form)
 __global__ void k_ebe_tangent(int nip, int64_t nelem, int64_t ip_off, int64_t nip_total, const int32_t *__restrict__ emat,
                               const int32_t *__restrict__ mat_kind, const double *__restrict__ mat_par,
-                              const double *__restrict__ state, double *w, uint8_t *pflag) {
+                              const double *__restrict__ state, double *w, int32_t *einfo) {
     for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < nelem; e += (int64_t)gridDim.x * blockDim.x) {
         const MatPar mp = load_mat(mat_kind, mat_par, emat[e]);
         int any = 0;
@@ -369,26 +466,38 @@ __global__ void k_ebe_tangent(int nip, int64_t nelem, int64_t ip_off, int64_t ni
 #pragma unroll
             for (int c = 0; c < 6; c++) w[(int64_t)c * nip_total + ip] = wv[c];
         }
-        pflag[e] = (uint8_t)any;
+        einfo[e] = (einfo[e] & ~EI_PLASTIC) | (any ? EI_PLASTIC : 0);
     }
 }
 
-__global__ void k_count_flags(int64_t n, int nip, const uint8_t *__restrict__ f, unsigned long long *out) {
+__global__ void k_count_flags(int64_t n, int nip, const int32_t *__restrict__ f, unsigned long long *out) {
     unsigned long long c = 0;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) c += f[i] ? nip : 0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) c += (f[i] & EI_PLASTIC) ? nip : 0;
     for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
     if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);   // integer count: order-independent
 }
 
-template <int NN, int ND, int NIP, int TA>
+template <int NN, int ND, int NIP, int TA, int NT>
 int ebe_configure(amaru_model *m) {
     int occ0 = 0, occ1 = 0;
-    const size_t s0 = EbeLayout<NN, ND, NIP, TA, false>::bytes, s1 = EbeLayout<NN, ND, NIP, TA, true>::bytes;
-    CUDA_CHECK(cudaFuncSetAttribute(k_ebe_apply<NN, ND, NIP, TA, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s0));
-    CUDA_CHECK(cudaFuncSetAttribute(k_ebe_apply<NN, ND, NIP, TA, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s1));
-    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ0, k_ebe_apply<NN, ND, NIP, TA, false>, EBE_NT, s0));
-    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ1, k_ebe_apply<NN, ND, NIP, TA, true>, EBE_NT, s1));
+    const size_t s0 = EbeLayout<NN, ND, NIP, TA, false, NT>::bytes, s1 = EbeLayout<NN, ND, NIP, TA, true, NT>::bytes;
+    auto k0 = k_ebe_apply<NN, ND, NIP, TA, false, NT>;
+    auto k1 = k_ebe_apply<NN, ND, NIP, TA, true, NT>;
+    CUDA_CHECK(cudaFuncSetAttribute(k0, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s0));
+    CUDA_CHECK(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s1));
+    CUDA_CHECK(cudaFuncSetAttribute(k0, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CUDA_CHECK(cudaFuncSetAttribute(k1, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ0, k0, NT, s0));
+    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ1, k1, NT, s1));
     return m->nsm * std::max(1, std::min(std::min(occ0, occ1), 8));
+}
+
+template <int NN, int ND, int NIP, int TA>
+void ebe_launch(amaru_model *m, const EbeArgs &a, int grid, bool mass) {
+    constexpr size_t s0 = EbeLayout<NN, ND, NIP, TA, false, EBE_NT>::bytes;
+    constexpr size_t s1 = EbeLayout<NN, ND, NIP, TA, true, EBE_NT>::bytes;
+    if (mass) k_ebe_apply<NN, ND, NIP, TA, true, EBE_NT><<<grid, EBE_NT, s1, m->stream>>>(a);
+    else k_ebe_apply<NN, ND, NIP, TA, false, EBE_NT><<<grid, EBE_NT, s0, m->stream>>>(a);
 }
 
 Ebe *ebe_of(amaru_model *m) { return static_cast<Ebe *>(m->ebe); }
@@ -425,17 +534,25 @@ void amaru_ebe_setup(amaru_model *m) {
         const int64_t nipb = b.nelem * b.nip;
         const int np = b.nd * b.nd + 1;
         CUDA_CHECK(cudaMalloc(&eb.d_geo, std::max<size_t>((size_t)np * nipb, 1) * sizeof(double)));
-        CUDA_CHECK(cudaMalloc(&eb.d_pflag, std::max<size_t>((size_t)b.nelem, 1)));
-        CUDA_CHECK(cudaMemsetAsync(eb.d_pflag, 0, std::max<size_t>((size_t)b.nelem, 1), m->stream));
+        AMARU_REQUIRE(m->nnodes < (int64_t)EC_NODE && m->nmats < EI_MAT, AMARU_ERR_UNSUPPORTED, "ebe: more than 2^28 nodes per GPU");
+        CUDA_CHECK(cudaMalloc(&eb.d_econn, std::max<size_t>((size_t)b.nelem * b.nn, 1) * sizeof(int32_t)));
+        CUDA_CHECK(cudaMalloc(&eb.d_einfo, std::max<size_t>((size_t)b.nelem, 1) * sizeof(int32_t)));
+        CUDA_CHECK(cudaMemsetAsync(eb.d_einfo, 0, std::max<size_t>((size_t)b.nelem, 1) * sizeof(int32_t), m->stream));
+        if (b.nelem > 0) {
+            const int ge = (int)std::min<int64_t>((b.nelem * b.nn + 255) / 256, (int64_t)m->nsm * 16);
+            k_ebe_econn<<<ge, 256, 0, m->stream>>>(b.nelem * b.nn, b.nd, m->nowned, b.d_conn, m->d_fixed, eb.d_econn);
+            k_ebe_einfo<<<ge, 256, 0, m->stream>>>(b.nelem, b.d_emat, nullptr, eb.d_einfo);
+            m->launches += 2;
+        }
         if (nipb == 0) continue;
         const int g = (int)std::min<int64_t>((nipb + 127) / 128, (int64_t)m->nsm * 16);
 #define GEO(NN, ND, NIP) k_ebe_geometry<NN, ND, NIP><<<g, 128, 0, m->stream>>>(b.nelem, b.d_conn, m->d_coords, b.d_dNdR, b.d_w, m->th, eb.d_geo, nipb)
         switch (b.shape) {
-        case AMARU_SHAPE_QUAD4: GEO(4, 2, 4); eb.grid = ebe_configure<4, 2, 4, 2>(m); break;
-        case AMARU_SHAPE_QUAD8: GEO(8, 2, 4); eb.grid = ebe_configure<8, 2, 4, 4>(m); break;
-        case AMARU_SHAPE_HEX8: GEO(8, 3, 8); eb.grid = ebe_configure<8, 3, 8, 2>(m); break;
-        case AMARU_SHAPE_HEX20: GEO(20, 3, 8); eb.grid = ebe_configure<20, 3, 8, 5>(m); break;
-        case AMARU_SHAPE_TET10: GEO(10, 3, 4); eb.grid = ebe_configure<10, 3, 4, 5>(m); break;
+        case AMARU_SHAPE_QUAD4: GEO(4, 2, 4); eb.grid = ebe_configure<4, 2, 4, 2, EBE_NT>(m); break;
+        case AMARU_SHAPE_QUAD8: GEO(8, 2, 4); eb.grid = ebe_configure<8, 2, 4, 4, EBE_NT>(m); break;
+        case AMARU_SHAPE_HEX8: GEO(8, 3, 8); eb.grid = ebe_configure<8, 3, 8, 2, EBE_NT>(m); break;
+        case AMARU_SHAPE_HEX20: GEO(20, 3, 8); eb.grid = ebe_configure<20, 3, 8, 5, EBE_NT>(m); break;
+        case AMARU_SHAPE_TET10: GEO(10, 3, 4); eb.grid = ebe_configure<10, 3, 4, 5, EBE_NT>(m); break;
         default: throw AmaruError{AMARU_ERR_UNSUPPORTED, "ebe: unsupported shape"};
         }
 #undef GEO
@@ -449,8 +566,8 @@ void amaru_ebe_destroy(amaru_model *m) {
     if (!E) return;
     for (EbeBatch &eb : E->b) {
         cudaFree(eb.d_geo);
-        cudaFree(eb.d_pflag);
-        cudaFree(eb.d_eown);
+        cudaFree(eb.d_econn);
+        cudaFree(eb.d_einfo);
     }
     cudaFree(E->d_w);
     cudaFree(E->d_dog);
@@ -464,8 +581,15 @@ void amaru_ebe_set_owned(amaru_model *m, int batch, const uint8_t *h_owned_sorte
     Ebe *E = ebe_of(m);
     Batch &b = m->batches[(size_t)batch];
     EbeBatch &eb = E->b[(size_t)batch];
-    if (!eb.d_eown) CUDA_CHECK(cudaMalloc(&eb.d_eown, std::max<size_t>((size_t)b.nelem, 1)));
-    CUDA_CHECK(cudaMemcpy(eb.d_eown, h_owned_sorted, (size_t)b.nelem, cudaMemcpyHostToDevice));
+    if (b.nelem == 0) return;
+    uint8_t *d_own = nullptr;
+    CUDA_CHECK(cudaMalloc(&d_own, (size_t)b.nelem));
+    CUDA_CHECK(cudaMemcpy(d_own, h_owned_sorted, (size_t)b.nelem, cudaMemcpyHostToDevice));
+    const int ge = (int)std::min<int64_t>((b.nelem + 255) / 256, (int64_t)m->nsm * 16);
+    k_ebe_einfo<<<ge, 256, 0, m->stream>>>(b.nelem, b.d_emat, d_own, eb.d_einfo);
+    m->launches++;
+    CUDA_CHECK(cudaStreamSynchronize(m->stream));
+    cudaFree(d_own);
 }
 
 // w planes from the current IP state (called by amaru_assemble_K: the operator then equals the assembled tangent)
@@ -478,8 +602,8 @@ void amaru_ebe_refresh(amaru_model *m) {
         if (b.nelem == 0) continue;
         const int g = (int)std::min<int64_t>((b.nelem + 127) / 128, (int64_t)m->nsm * 16);
         k_ebe_tangent<<<g, 128, 0, m->stream>>>(b.nip, b.nelem, b.ip_off, m->nip_total, b.d_emat, m->d_mat_kind, m->d_mat_par,
-                                                m->d_state, E->d_w, E->b[i].d_pflag);
-        k_count_flags<<<g, 128, 0, m->stream>>>(b.nelem, b.nip, E->b[i].d_pflag, reinterpret_cast<unsigned long long *>(E->d_nplastic));
+                                                m->d_state, E->d_w, E->b[i].d_einfo);
+        k_count_flags<<<g, 128, 0, m->stream>>>(b.nelem, b.nip, E->b[i].d_einfo, reinterpret_cast<unsigned long long *>(E->d_nplastic));
         m->launches += 2;
     }
     CUDA_CHECK(cudaGetLastError());
@@ -498,14 +622,14 @@ void amaru_ebe_apply(amaru_model *m, const double *x, double *y, int mask, int d
         for (size_t c = 0; c + 1 < b.color_off.size(); c++) nl += b.color_off[c + 1] > b.color_off[c];
     EbeArgs a;
     a.dog = E->d_dog; a.w = E->d_w; a.nip_total = m->nip_total; a.sa = m->sysA; a.sb = m->sysB;
-    a.x = x; a.y = y; a.fixed = m->d_fixed; a.mask = mask; a.nowned = m->nowned;
+    a.x = x; a.y = y; a.mask = mask; a.nmats = m->nmats;
     a.partial = m->d_partial; a.scal = m->d_scal; a.dot = dot; a.finalize = finalize; a.check_done = check_done;
     a.first = 1;
     for (size_t i = 0; i < m->batches.size(); i++) {
         Batch &b = m->batches[i];
         EbeBatch &eb = E->b[i];
         AMARU_REQUIRE(!mass || b.d_rho != nullptr, AMARU_ERR_ARG, "ebe: mass term without densities (call amaru_assemble_M)");
-        a.conn = b.d_conn; a.emat = b.d_emat; a.eown = eb.d_eown; a.pflag = eb.d_pflag; a.geo = eb.d_geo;
+        a.econn = eb.d_econn; a.einfo = eb.d_einfo; a.geo = eb.d_geo;
         a.nipb = b.nelem * b.nip; a.ip_off = b.ip_off; a.dNdR = b.d_dNdR; a.Nf = b.d_N; a.rho = b.d_rho;
         for (size_t c = 0; c + 1 < b.color_off.size(); c++) {
             const int64_t n = b.color_off[c + 1] - b.color_off[c];
@@ -516,20 +640,14 @@ void amaru_ebe_apply(amaru_model *m, const double *x, double *y, int mask, int d
             a.last = il == nl;
             const int epb = EBE_NT / b.nip;
             const int grid = (int)std::min<int64_t>((n + epb - 1) / epb, eb.grid);
-#define APPLY(NN, ND, NIP, TA)                                                                                         \
-    do {                                                                                                               \
-        if (mass) k_ebe_apply<NN, ND, NIP, TA, true><<<grid, EBE_NT, EbeLayout<NN, ND, NIP, TA, true>::bytes, m->stream>>>(a);   \
-        else k_ebe_apply<NN, ND, NIP, TA, false><<<grid, EBE_NT, EbeLayout<NN, ND, NIP, TA, false>::bytes, m->stream>>>(a);      \
-    } while (0)
             switch (b.shape) {
-            case AMARU_SHAPE_QUAD4: APPLY(4, 2, 4, 2); break;
-            case AMARU_SHAPE_QUAD8: APPLY(8, 2, 4, 4); break;
-            case AMARU_SHAPE_HEX8: APPLY(8, 3, 8, 2); break;
-            case AMARU_SHAPE_HEX20: APPLY(20, 3, 8, 5); break;
-            case AMARU_SHAPE_TET10: APPLY(10, 3, 4, 5); break;
+            case AMARU_SHAPE_QUAD4: ebe_launch<4, 2, 4, 2>(m, a, grid, mass); break;
+            case AMARU_SHAPE_QUAD8: ebe_launch<8, 2, 4, 4>(m, a, grid, mass); break;
+            case AMARU_SHAPE_HEX8: ebe_launch<8, 3, 8, 2>(m, a, grid, mass); break;
+            case AMARU_SHAPE_HEX20: ebe_launch<20, 3, 8, 5>(m, a, grid, mass); break;
+            case AMARU_SHAPE_TET10: ebe_launch<10, 3, 4, 5>(m, a, grid, mass); break;
             default: throw AmaruError{AMARU_ERR_UNSUPPORTED, "ebe: unsupported shape"};
             }
-#undef APPLY
             m->launches++;
             a.first = 0;
         }

@@ -11,7 +11,7 @@ dm = L.DeviceModel(model.flatten(), eqid, eqid.size, nu)
 dm.state_backup(); dm.assemble_K()
 dU = 0.1 * Uex
 dm.update_state(dU); dm.assemble_K()
-for op in ("csr", "ebe"):
+for op in (sys.argv[2].split(",") if len(sys.argv) > 2 else ("csr", "ebe")):
     dm.set_operator(op)
     print(op, dm.spmv_kernel, "bytes", dm.spmv_bytes)
     for kind, nm in ((0, "operator+dot"), (3, "cg_update"), (4, "cg_pupdate"), (1, "assemble_K"), (2, "update")):
