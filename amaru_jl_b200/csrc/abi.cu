@@ -238,6 +238,31 @@ amaru_model *create_impl(const CreateArgs &a) {
     return mp.release();
 }
 
+// An element is counted (p.Ap of the matrix-free operator) on the lowest rank that owns one of its nodes — the rank whose
+// copy of the element's IP state is authoritative (amaru_jl_b200/partition.py).  Node owners follow from the halo lists:
+// local nodes below nowned are ours, every ghost range belongs to one neighbour.
+void set_element_ownership(amaru_model *m, const int32_t *conn, int nneigh, const int32_t *neigh_rank,
+                           const int64_t *recv_start, const int64_t *recv_count) {
+    std::vector<int32_t> owner((size_t)m->nnodes, m->rank);
+    for (int q = 0; q < nneigh; q++)
+        for (int64_t i = 0; i < recv_count[q]; i++) owner[(size_t)(recv_start[q] + i)] = neigh_rank[q];
+    int64_t coff = 0;
+    for (size_t bi = 0; bi < m->batches.size(); bi++) {
+        Batch &B = m->batches[bi];
+        std::vector<int64_t> perm((size_t)B.nelem);
+        if (B.nelem) CUDA_CHECK(cudaMemcpy(perm.data(), B.d_perm, perm.size() * sizeof(int64_t), cudaMemcpyDeviceToHost));
+        std::vector<uint8_t> own((size_t)B.nelem);
+        for (int64_t s = 0; s < B.nelem; s++) {
+            const int32_t *c = conn + coff + perm[(size_t)s] * B.nn;
+            int32_t lo = owner[(size_t)c[0]];
+            for (int a = 1; a < B.nn; a++) lo = std::min(lo, owner[(size_t)c[a]]);
+            own[(size_t)s] = (uint8_t)(lo == m->rank);
+        }
+        amaru_ebe_set_owned(m, (int)bi, own.data());
+        coff += B.nelem * B.nn;
+    }
+}
+
 void free_model(amaru_model *m) {
     cudaSetDevice(m->device);
     if (m->stream) cudaStreamSynchronize(m->stream);
@@ -353,7 +378,10 @@ int amaru_create_partitioned(int ndim, int stressmodel, double thickness, int64_
                      elem_mat, nmats, mat_kind, mat_params, eqid, nullptr, ndofs, nu, device, rank, nranks};
         amaru_model *m = create_impl(a);
         try {
-            if (nranks > 1) amaru_comm_setup(m, nneigh, neigh_rank, send_ptr, send_nodes, recv_start, recv_count, nccl_uid);
+            if (nranks > 1) {
+                amaru_comm_setup(m, nneigh, neigh_rank, send_ptr, send_nodes, recv_start, recv_count, nccl_uid);
+                set_element_ownership(m, conn, nneigh, neigh_rank, recv_start, recv_count);
+            }
         } catch (...) {
             free_model(m);
             throw;

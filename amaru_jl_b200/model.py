@@ -230,7 +230,9 @@ class FEModel:
         return np.nonzero(select(flt, self.coords))[0]
 
     # ------------------------------------------------------------------ configure_dofs! (bc.jl:198-233)
-    def configure_dofs(self, bcs):
+    def configure_dofs(self, bcs, native=True):
+        """``native=False`` numbers the dofs in numpy instead of through ``amaru_configure_dofs`` (the CPU reference arm of
+        bench.py must not load the product library)."""
         nd = self.ndim
         presc = np.zeros((self.nnodes, nd), dtype=bool)
         setup = []
@@ -256,8 +258,16 @@ class FEModel:
                         presc[np.unique(self.conn[sel]), ESSENTIAL.index(key)] = True
             else:
                 raise AmaruError(f"unsupported boundary condition {type(bc).__name__}")
-        from . import lib as L                                        # node-major, ux,uy,uz per node; stable split
-        eq, nu = L.configure_dofs(presc)                              # (bc.jl:220-224) in C++ behind the ABI
+        if native:
+            from . import lib as L                                    # node-major, ux,uy,uz per node; stable split
+            eq, nu = L.configure_dofs(presc)                          # (bc.jl:220-224) in C++ behind the ABI
+        else:
+            flat = presc.reshape(-1)
+            nu = int((~flat).sum())
+            eq = np.empty(flat.size, dtype=np.int32)
+            eq[~flat] = np.arange(nu, dtype=np.int32)
+            eq[flat] = nu + np.arange(flat.size - nu, dtype=np.int32)
+            eq = eq.reshape(presc.shape)
         return eq, nu, setup
 
     # ------------------------------------------------------------------ get_bc_vals (bc.jl:237-249)
