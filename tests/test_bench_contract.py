@@ -15,7 +15,7 @@ def run(args, env=None):
 
 
 def test_reference_arm_prints_one_json_line():
-    r = run(["--impl", "reference", "--gpus", "1", "--steps", "1", "--warmup", "0", "--cpu-size", "4"])
+    r = run(["--impl", "reference", "--gpus", "1", "--steps", "1", "--warmup", "0", "--ref-size", "4", "--cpu-direct-size", "3"])
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
     assert len(lines) == 1
@@ -25,11 +25,14 @@ def test_reference_arm_prints_one_json_line():
     assert d["value"] > 0 and d["ms_per_step"] > 0 and d["vs_baseline"] is None and "workload" in d["config"]
     cb = d["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "HEX20 4^3" in cb["sample"]
+    assert "Jacobi-PCG" in cb["sample"] and "4x4x4" in d["config"]["workload"]          # same-algorithm CPU leg, sample named
+    assert cb["direct"]["value"] > 0 and "SuperLU" in cb["direct"]["sample"]              # the reference's own direct solve beside it
+    assert not any("libamaru_b200" in x for x in d["repo_so_mapped"])                     # the CPU arm never maps the product library
     assert d["e2e"] == {"value": d["value"], "unit": "elements/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
 
 def test_reference_arm_other_ranks_stay_silent():
-    r = run(["--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0", "--cpu-size", "4"],
+    r = run(["--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0", "--ref-size", "4"],
             env={"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"})
     assert r.returncode == 0 and r.stdout.strip() == ""
 
