@@ -8,6 +8,7 @@
 #include <numeric>
 
 #include "amaru_internal.h"
+#include "partition.h"
 
 namespace {
 
@@ -41,6 +42,18 @@ T *upload(const T *h, size_t n) {
 
 void use_device(const amaru_model *m) { CUDA_CHECK(cudaSetDevice(m->device)); }
 
+template <int N>
+struct EventSet {   // CUDA events released on every exit path
+    cudaEvent_t ev[N] = {};
+    EventSet() {
+        for (auto &e : ev) CUDA_CHECK(cudaEventCreate(&e));
+    }
+    ~EventSet() {
+        for (auto &e : ev)
+            if (e) cudaEventDestroy(e);
+    }
+};
+
 const char *status_text(int st) {
     switch (st) {
     case AMARU_FAIL_MATERIAL: return "VonMisses: Negative value for √J2D";   // von-mises.jl:146
@@ -61,27 +74,9 @@ int read_status(amaru_model *m) {
 }
 void reset_status(amaru_model *m) { CUDA_CHECK(cudaMemsetAsync(m->d_status, 0, sizeof(int), m->stream)); }
 
-struct CreateArgs {
-    int ndim, stressmodel;
-    double thickness;
-    int64_t nnodes, nowned;
-    const double *coords;
-    int nbatches;
-    const int32_t *batch_shape;
-    const int64_t *batch_nelem;
-    const int32_t *conn;
-    const int32_t *elem_mat;
-    int nmats;
-    const int32_t *mat_kind;
-    const double *mat_params;
-    const int32_t *eqid;
-    const uint8_t *prescribed;   // optional (partitioned); else eqid >= nu
-    int64_t ndofs, nu;
-    int device;
-    int rank, nranks;
-};
+}  // namespace
 
-amaru_model *create_impl(const CreateArgs &a) {
+amaru_model *amaru_create_impl(const CreateArgs &a) {
     AMARU_REQUIRE(a.ndim == 2 || a.ndim == 3, AMARU_ERR_ARG, "amaru_create: ndim must be 2 or 3");
     AMARU_REQUIRE(a.stressmodel == AMARU_STRESS_D3 || a.stressmodel == AMARU_STRESS_PLANESTRAIN, AMARU_ERR_UNSUPPORTED,
                   "amaru_create: only the d3 / planestrain stress models are on the B200 hot path (no CPU fallback)");
@@ -99,8 +94,13 @@ amaru_model *create_impl(const CreateArgs &a) {
                       AMARU_ERR_UNSUPPORTED, "amaru_create: material outside the hot path (LinearElastic, VonMises, DruckerPrager)");
     }
 
-    std::unique_ptr<amaru_model> mp(new amaru_model());
-    amaru_model *m = mp.get();
+    // on a throw below, release every device allocation made so far (not only the struct)
+    struct ModelGuard {
+        amaru_model *m;
+        ~ModelGuard() { if (m) amaru_free_model(m); }
+        amaru_model *release() { amaru_model *r = m; m = nullptr; return r; }
+    } mp{new amaru_model()};
+    amaru_model *m = mp.m;
     m->device = a.device;
     CUDA_CHECK(cudaSetDevice(a.device));
     cudaDeviceProp prop;
@@ -238,6 +238,8 @@ amaru_model *create_impl(const CreateArgs &a) {
     return mp.release();
 }
 
+namespace {
+
 // An element is counted (p.Ap of the matrix-free operator) on the lowest rank that owns one of its nodes — the rank whose
 // copy of the element's IP state is authoritative (amaru_jl_b200/partition.py).  Node owners follow from the halo lists:
 // local nodes below nowned are ours, every ghost range belongs to one neighbour.
@@ -274,8 +276,9 @@ void free_model(amaru_model *m) {
         cudaFree(B.d_rho); cudaFree(B.d_dNdR); cudaFree(B.d_N); cudaFree(B.d_w);
     }
     cudaFree(m->d_Abuf);
+    if (m->io_shared && m->rank > 0) m->d_U = m->d_F = m->d_U0 = m->d_F0 = nullptr;   // they live on the group's first GPU
     for (void *p : {(void *)m->d_coords, (void *)m->d_eqid, (void *)m->d_fixed, (void *)m->d_mat_kind, (void *)m->d_mat_par,
-                    (void *)m->d_rowptr, (void *)m->d_col, (void *)m->d_diag, (void *)m->d_K, (void *)m->d_M,
+                    (void *)m->d_rowptr, (void *)m->d_col, (void *)m->d_diag, (void *)m->d_K, (void *)m->d_Ksave, (void *)m->d_M,
                     (void *)m->d_Minv, (void *)m->d_state, (void *)m->d_statebk, (void *)m->d_x, (void *)m->d_r,
                     (void *)m->d_z, (void *)m->d_p, (void *)m->d_q, (void *)m->d_b, (void *)m->d_f, (void *)m->d_io,
                     (void *)m->d_U, (void *)m->d_F, (void *)m->d_U0, (void *)m->d_F0, (void *)m->d_tiles, (void *)m->d_tmeta,
@@ -295,6 +298,13 @@ int solve_device(amaru_model *m, double cg_rtol, int cg_maxit, int precond, Solv
     if (m->nranks == 1) {
         amaru_nodes_to_eq(m, m->d_x, m->d_U, 1);   // U[1:nu]     .= U1   (solver.jl:74)
         amaru_nodes_to_eq(m, m->d_q, m->d_F, 2);   // F[nu+1:end] .= F2   (solver.jl:75)
+    } else if (m->io_shared) {
+        // one process, d_U / d_F are ONE pair of ABI-order vectors on the first GPU: once every rank has read its inputs,
+        // each rank stores the entries of the rows it owns straight into them over NVLink (disjoint, no reduction)
+        amaru_group_barrier(m);
+        amaru_nodes_to_eq(m, m->d_x, m->d_U, 1);
+        amaru_nodes_to_eq(m, m->d_q, m->d_F, 2);
+        amaru_group_barrier(m);
     } else {
         // every rank contributes the entries of the rows it owns; one all-reduce per vector rebuilds the global ones
         const size_t bytes = (size_t)m->ndofs * sizeof(double);
@@ -318,6 +328,14 @@ int update_device(amaru_model *m) {
     reset_status(m);
     amaru_eq_to_nodes(m, m->d_U, m->d_x);
     amaru_launch_update(m, m->d_x, m->d_f, 0);
+    if (m->io_shared) {   // every dof is owned by exactly one rank: the owners' stores rebuild the ABI vector on the first GPU
+        amaru_group_barrier(m);                      // every rank has read ΔU from d_U
+        amaru_nodes_to_eq(m, m->d_f, m->d_F, 0);
+        amaru_group_barrier(m);
+        const int st = read_status(m);               // the caller takes the maximum over the ranks
+        if (st) return st;
+        return amaru_check_nan(m, m->d_f, m->nowned * m->nd) ? AMARU_FAIL_NAN : AMARU_OK;
+    }
     CUDA_CHECK(cudaMemsetAsync(m->d_F, 0, (size_t)m->ndofs * sizeof(double), m->stream));
     amaru_nodes_to_eq(m, m->d_f, m->d_F, 0);
     if (m->nranks > 1) {
@@ -333,6 +351,20 @@ int update_device(amaru_model *m) {
 
 }  // namespace
 
+// internals shared with group.cu (multi-GPU handles of one process)
+void amaru_set_element_ownership(amaru_model *m, const int32_t *conn, int nneigh, const int32_t *neigh_rank,
+                                 const int64_t *recv_start, const int64_t *recv_count) {
+    set_element_ownership(m, conn, nneigh, neigh_rank, recv_start, recv_count);
+}
+void amaru_free_model(amaru_model *m) { free_model(m); }
+int amaru_solve_device(amaru_model *m, double cg_rtol, int cg_maxit, int precond, SolveInfo &info) {
+    return solve_device(m, cg_rtol, cg_maxit, precond, info);
+}
+int amaru_update_device(amaru_model *m) { return update_device(m); }
+const char *amaru_status_text(int st) { return status_text(st); }
+int amaru_read_status(amaru_model *m) { return read_status(m); }
+void amaru_reset_status(amaru_model *m) { reset_status(m); }
+
 extern "C" {
 
 int amaru_device_count(void) {
@@ -346,15 +378,49 @@ const char *amaru_version(void) { return "amaru_b200 0.1 (sm_100a)"; }
 int amaru_create(int ndim, int stressmodel, double thickness, int64_t nnodes, const double *coords, int nbatches,
                  const int32_t *batch_shape, const int64_t *batch_nelem, const int32_t *conn, const int32_t *elem_mat,
                  int nmats, const int32_t *mat_kind, const double *mat_params, const int32_t *eqid, int64_t ndofs,
-                 int64_t nu, int device, amaru_model **out, char *msg, int msglen) {
+                 int64_t nu, int ngpus, const int32_t *devices, int partitioner, amaru_model **out, char *msg, int msglen) {
     return guarded(msg, msglen, [&]() {
         AMARU_REQUIRE(out != nullptr, AMARU_ERR_ARG, "amaru_create: out is NULL");
         *out = nullptr;
         AMARU_REQUIRE(ndofs == nnodes * ndim, AMARU_ERR_ARG, "amaru_create: ndofs must equal nnodes*ndim");
         AMARU_REQUIRE(nu >= 0 && nu <= ndofs, AMARU_ERR_ARG, "amaru_create: nu out of range");
+        AMARU_REQUIRE(ngpus >= 1 && ngpus <= 16, AMARU_ERR_ARG, "amaru_create: ngpus must be 1..16");
+        AMARU_REQUIRE(partitioner == AMARU_PARTITION_RCB || partitioner == AMARU_PARTITION_METIS, AMARU_ERR_ARG, "amaru_create: bad partitioner");
         CreateArgs a{ndim, stressmodel, thickness, nnodes, nnodes, coords, nbatches, batch_shape, batch_nelem, conn,
-                     elem_mat, nmats, mat_kind, mat_params, eqid, nullptr, ndofs, nu, device, 0, 1};
-        *out = create_impl(a);
+                     elem_mat, nmats, mat_kind, mat_params, eqid, nullptr, ndofs, nu, devices ? devices[0] : 0, 0, 1};
+        if (ngpus > 1) {
+            AMARU_REQUIRE(nnodes > 0 && nbatches > 0 && nmats > 0 && coords && conn && elem_mat && mat_kind && mat_params && eqid &&
+                              batch_shape && batch_nelem, AMARU_ERR_ARG, "amaru_create: empty model / null pointer");
+            return amaru_group_create(a, ngpus, devices, partitioner, out, msg, msglen);
+        }
+        *out = amaru_create_impl(a);
+        return AMARU_OK;
+    });
+}
+
+int amaru_partition_elements_abi(int partitioner, int nparts, int64_t nnodes, const double *coords, int nbatches,
+                                 const int32_t *batch_shape, const int64_t *batch_nelem, const int32_t *conn, int32_t *elem_part,
+                                 char *msg, int msglen) {
+    return guarded(msg, msglen, [&]() {
+        AMARU_REQUIRE(coords && batch_shape && batch_nelem && conn && elem_part && nparts >= 1 && nbatches > 0, AMARU_ERR_ARG,
+                      "amaru_partition_elements: bad argument");
+        AMARU_REQUIRE(partitioner == AMARU_PARTITION_RCB || partitioner == AMARU_PARTITION_METIS, AMARU_ERR_ARG, "bad partitioner");
+        std::vector<int> nn((size_t)nbatches);
+        std::vector<const int32_t *> connp((size_t)nbatches);
+        int64_t coff = 0, total = 0;
+        for (int b = 0; b < nbatches; b++) {
+            ShapeInfo si;
+            AMARU_REQUIRE(amaru_shape_info(batch_shape[b], si), AMARU_ERR_UNSUPPORTED, "unknown cell shape");
+            nn[(size_t)b] = si.nn;
+            connp[(size_t)b] = conn + coff;
+            for (int64_t i = 0; i < batch_nelem[b] * si.nn; i++)
+                AMARU_REQUIRE(conn[coff + i] >= 0 && conn[coff + i] < nnodes, AMARU_ERR_ARG, "node id out of range");
+            coff += batch_nelem[b] * si.nn;
+            total += batch_nelem[b];
+        }
+        std::vector<int32_t> part;
+        amaru_partition_elements(partitioner, nparts, nnodes, coords, nbatches, nn.data(), batch_shape, batch_nelem, connp.data(), part);
+        std::memcpy(elem_part, part.data(), (size_t)total * sizeof(int32_t));
         return AMARU_OK;
     });
 }
@@ -376,7 +442,7 @@ int amaru_create_partitioned(int ndim, int stressmodel, double thickness, int64_
                       "amaru_create_partitioned: null halo lists");
         CreateArgs a{ndim, stressmodel, thickness, nnodes, nowned, coords, nbatches, batch_shape, batch_nelem, conn,
                      elem_mat, nmats, mat_kind, mat_params, eqid, nullptr, ndofs, nu, device, rank, nranks};
-        amaru_model *m = create_impl(a);
+        amaru_model *m = amaru_create_impl(a);
         try {
             if (nranks > 1) {
                 amaru_comm_setup(m, nneigh, neigh_rank, send_ptr, send_nodes, recv_start, recv_count, nccl_uid);
@@ -393,19 +459,22 @@ int amaru_create_partitioned(int ndim, int stressmodel, double thickness, int64_
 
 int amaru_destroy(amaru_model *m) {
     if (!m) return AMARU_ERR_ARG;
+    if (m->grp) return amaru_group_destroy(m);
     free_model(m);
     return AMARU_OK;
 }
 
 int64_t amaru_nip_total(const amaru_model *m) { return m ? m->nip_total : -1; }
-int64_t amaru_nnz(const amaru_model *m) { return m ? m->nblk * m->nd * m->nd : -1; }
-int64_t amaru_nblocks(const amaru_model *m) { return m ? m->nblk : -1; }
-int amaru_ncolors(const amaru_model *m) { return m ? m->ncolors : -1; }
-int64_t amaru_launch_count(const amaru_model *m) { return m ? m->launches : -1; }
+int64_t amaru_nnz(const amaru_model *m) { return m ? amaru_nblocks(m) * m->nd * m->nd : -1; }
+int64_t amaru_nblocks(const amaru_model *m) { return !m ? -1 : (m->grp ? amaru_group_sum(m, 0) : m->nblk); }
+int amaru_ncolors(const amaru_model *m) { return !m ? -1 : (m->grp ? amaru_group_part(m, 0)->ncolors : m->ncolors); }
+int64_t amaru_launch_count(const amaru_model *m) { return !m ? -1 : (m->grp ? amaru_group_sum(m, 1) : m->launches); }
+int amaru_ngpus(const amaru_model *m) { return !m ? -1 : (m->grp ? m->nranks : 1); }
 int64_t amaru_spmv_bytes(const amaru_model *m) {
     if (!m) return -1;
+    if (m->grp) return amaru_spmv_bytes(amaru_group_part(m, 0));
     const int64_t b2 = (int64_t)m->nd * m->nd, n = m->nowned * m->nd;
-    if (m->op_ebe) return amaru_ebe_bytes(m);
+    if (m->op_ebe && !m->blended) return amaru_ebe_bytes(m);
     if (m->use_sym)   // CG product from the symmetric storage: upper blocks + records + x once + y zeroed and reduced into once
         return m->nublk * b2 * 8 + m->sym_meta_bytes + 8 * n + 16 * n;
     const int64_t meta = m->use_tma ? m->spmv_meta_bytes : m->nblk * 4 + (m->nowned + 1) * 4 + n;   // + fixed mask
@@ -414,7 +483,8 @@ int64_t amaru_spmv_bytes(const amaru_model *m) {
 
 const char *amaru_spmv_kernel(const amaru_model *m) {
     if (!m) return "";
-    if (m->op_ebe) return amaru_ebe_kernel(m);
+    if (m->grp) return amaru_spmv_kernel(amaru_group_part(m, 0));
+    if (m->op_ebe && !m->blended) return amaru_ebe_kernel(m);
     if (m->use_sym) return m->nd == 3 ? "k_spmv_sym<3,true>" : "k_spmv_sym<2,true>";
     if (m->use_tma) return m->spmv_ver == 2 ? (m->nd == 3 ? "k_spmv_stream2<3,true>" : "k_spmv_stream2<2,true>")
                                             : (m->nd == 3 ? "k_spmv_stream<3,true>" : "k_spmv_stream<2,true>");
@@ -425,6 +495,9 @@ int amaru_set_state(amaru_model *m, const double *sigma, const double *eps, cons
                     char *msg, int msglen) {
     return guarded(msg, msglen, [&]() {
         AMARU_REQUIRE(m, AMARU_ERR_ARG, "null handle");
+        if (m->grp)
+            return amaru_group_state(m, true, const_cast<double *>(sigma), const_cast<double *>(eps), const_cast<double *>(epa),
+                                     const_cast<double *>(dlam), msg, msglen);
         use_device(m);
         const int64_t n = m->nip_total;
         struct F { const double *h; int plane0, ncomp; } fields[4] = {{sigma, 0, 6}, {eps, 6, 6}, {epa, 12, 1}, {dlam, 13, 1}};
@@ -441,6 +514,7 @@ int amaru_set_state(amaru_model *m, const double *sigma, const double *eps, cons
 int amaru_get_state(amaru_model *m, double *sigma, double *eps, double *epa, double *dlam, char *msg, int msglen) {
     return guarded(msg, msglen, [&]() {
         AMARU_REQUIRE(m, AMARU_ERR_ARG, "null handle");
+        if (m->grp) return amaru_group_state(m, false, sigma, eps, epa, dlam, msg, msglen);
         use_device(m);
         const int64_t n = m->nip_total;
         struct F { double *h; int plane0, ncomp; } fields[4] = {{sigma, 0, 6}, {eps, 6, 6}, {epa, 12, 1}, {dlam, 13, 1}};
@@ -456,6 +530,7 @@ int amaru_get_state(amaru_model *m, double *sigma, double *eps, double *epa, dou
 
 int amaru_state_backup(amaru_model *m) {
     if (!m) return AMARU_ERR_ARG;
+    if (m->grp) return amaru_group_simple(m, 0, 0, 0, nullptr, 0);
     cudaSetDevice(m->device);
     const size_t bytes = (size_t)AMARU_NSTATE * m->nip_total * sizeof(double);
     if (cudaMemcpyAsync(m->d_statebk, m->d_state, bytes, cudaMemcpyDeviceToDevice, m->stream) != cudaSuccess) return AMARU_ERR_CUDA;
@@ -464,6 +539,7 @@ int amaru_state_backup(amaru_model *m) {
 
 int amaru_state_restore(amaru_model *m) {
     if (!m) return AMARU_ERR_ARG;
+    if (m->grp) return amaru_group_simple(m, 1, 0, 0, nullptr, 0);
     cudaSetDevice(m->device);
     const size_t bytes = (size_t)AMARU_NSTATE * m->nip_total * sizeof(double);
     if (cudaMemcpyAsync(m->d_state, m->d_statebk, bytes, cudaMemcpyDeviceToDevice, m->stream) != cudaSuccess) return AMARU_ERR_CUDA;
@@ -473,9 +549,11 @@ int amaru_state_restore(amaru_model *m) {
 int amaru_assemble_K(amaru_model *m, char *msg, int msglen) {
     return guarded(msg, msglen, [&]() {
         AMARU_REQUIRE(m, AMARU_ERR_ARG, "null handle");
+        if (m->grp) return amaru_group_simple(m, 2, 0, 0, msg, msglen);
         use_device(m);
         reset_status(m);
         amaru_launch_assemble(m, 0);
+        m->blended = false;
         amaru_combine_matrix(m);
         amaru_ebe_refresh(m);
         if (m->nranks > 1) amaru_allreduce_max_int(m, m->d_status);
@@ -485,9 +563,36 @@ int amaru_assemble_K(amaru_model *m, char *msg, int msglen) {
     });
 }
 
+int amaru_tangent_save(amaru_model *m, char *msg, int msglen) {
+    return guarded(msg, msglen, [&]() {
+        AMARU_REQUIRE(m, AMARU_ERR_ARG, "null handle");
+        if (m->grp) return amaru_group_simple(m, 6, 0, 0, msg, msglen);
+        use_device(m);
+        const size_t bytes = (size_t)m->nblk * m->nd * m->nd * sizeof(double);
+        if (!m->d_Ksave) CUDA_CHECK(cudaMalloc(&m->d_Ksave, bytes + 256));
+        CUDA_CHECK(cudaMemcpyAsync(m->d_Ksave, m->d_K, bytes, cudaMemcpyDeviceToDevice, m->stream));
+        return AMARU_OK;
+    });
+}
+
+int amaru_tangent_blend(amaru_model *m, double a1, double a2, char *msg, int msglen) {
+    return guarded(msg, msglen, [&]() {
+        AMARU_REQUIRE(m, AMARU_ERR_ARG, "null handle");
+        if (m->grp) return amaru_group_simple(m, 7, a1, a2, msg, msglen);
+        use_device(m);
+        AMARU_REQUIRE(m->d_Ksave != nullptr, AMARU_ERR_ARG, "amaru_tangent_blend: call amaru_tangent_save first");
+        if (a1 == 0.0 && a2 == 1.0) return AMARU_OK;   // :BE — K2 itself, the per-IP tangent data still describes it
+        amaru_axpby(m, m->nblk * m->nd * m->nd, a1, m->d_Ksave, a2, m->d_K, m->d_K);
+        m->blended = true;
+        amaru_combine_matrix(m);
+        return AMARU_OK;
+    });
+}
+
 int amaru_assemble_M(amaru_model *m, const double *rho, char *msg, int msglen) {
     return guarded(msg, msglen, [&]() {
         AMARU_REQUIRE(m && rho, AMARU_ERR_ARG, "null argument");
+        if (m->grp) return amaru_group_assemble_M(m, rho, msg, msglen);
         use_device(m);
         reset_status(m);
         if (!m->d_M) CUDA_CHECK(cudaMalloc(&m->d_M, (size_t)m->nblk * m->nd * m->nd * sizeof(double) + 256));
@@ -500,6 +605,8 @@ int amaru_assemble_M(amaru_model *m, const double *rho, char *msg, int msglen) {
             B.d_rho = upload(r.data(), r.size());
         }
         amaru_launch_assemble(m, 1);
+        if (m->sysB != 0.0) amaru_combine_matrix(m);    // a*K + b*M in use: keep it in step with the new M
+        if (m->nranks > 1) amaru_allreduce_max_int(m, m->d_status);   // every rank takes the same exit
         const int st = read_status(m);
         if (st) throw AmaruError{st, status_text(st)};
         return AMARU_OK;
@@ -509,6 +616,7 @@ int amaru_assemble_M(amaru_model *m, const double *rho, char *msg, int msglen) {
 int amaru_set_system_matrix(amaru_model *m, double a, double b, char *msg, int msglen) {
     return guarded(msg, msglen, [&]() {
         AMARU_REQUIRE(m, AMARU_ERR_ARG, "null handle");
+        if (m->grp) return amaru_group_simple(m, 3, a, b, msg, msglen);
         use_device(m);
         m->sysA = a;
         m->sysB = b;
@@ -521,7 +629,7 @@ int amaru_set_system_matrix(amaru_model *m, double a, double b, char *msg, int m
 int amaru_get_csr(amaru_model *m, int64_t *rowptr, int32_t *colind, double *val, char *msg, int msglen) {
     return guarded(msg, msglen, [&]() {
         AMARU_REQUIRE(m && rowptr && colind, AMARU_ERR_ARG, "null argument");
-        AMARU_REQUIRE(m->nranks == 1, AMARU_ERR_UNSUPPORTED, "amaru_get_csr: single-GPU handles only");
+        AMARU_REQUIRE(m->nranks == 1 && !m->grp, AMARU_ERR_UNSUPPORTED, "amaru_get_csr: single-GPU handles only");
         use_device(m);
         const int bs = m->nd, b2 = bs * bs;
         std::vector<double> K;
@@ -566,6 +674,7 @@ int amaru_solve(amaru_model *m, double *U, double *F, double cg_rtol, int cg_max
         AMARU_REQUIRE(m && U && F, AMARU_ERR_ARG, "null argument");
         AMARU_REQUIRE(cg_rtol > 0 && cg_maxit > 0, AMARU_ERR_ARG, "amaru_solve: cg_rtol and cg_maxit must be > 0");
         AMARU_REQUIRE(precond == AMARU_PRECOND_JACOBI || precond == AMARU_PRECOND_BLOCK_JACOBI, AMARU_ERR_ARG, "bad preconditioner");
+        if (m->grp) return amaru_group_solve(m, U, F, cg_rtol, cg_maxit, precond, iters, relres, msg, msglen);
         use_device(m);
         const size_t bytes = (size_t)m->ndofs * sizeof(double);
         CUDA_CHECK(cudaMemcpyAsync(m->d_U, U, bytes, cudaMemcpyHostToDevice, m->stream));
@@ -587,6 +696,7 @@ int amaru_solve(amaru_model *m, double *U, double *F, double cg_rtol, int cg_max
 int amaru_update_state(amaru_model *m, const double *dU, double *dFin, char *msg, int msglen) {
     return guarded(msg, msglen, [&]() {
         AMARU_REQUIRE(m && dU && dFin, AMARU_ERR_ARG, "null argument");
+        if (m->grp) return amaru_group_update(m, dU, dFin, 0, msg, msglen);
         use_device(m);
         const size_t bytes = (size_t)m->ndofs * sizeof(double);
         CUDA_CHECK(cudaMemcpyAsync(m->d_U, dU, bytes, cudaMemcpyHostToDevice, m->stream));
@@ -601,10 +711,12 @@ int amaru_update_state(amaru_model *m, const double *dU, double *dFin, char *msg
 int amaru_internal_forces(amaru_model *m, double *Fin, char *msg, int msglen) {
     return guarded(msg, msglen, [&]() {
         AMARU_REQUIRE(m && Fin, AMARU_ERR_ARG, "null argument");
+        if (m->grp) return amaru_group_update(m, nullptr, Fin, 1, msg, msglen);
         use_device(m);
         amaru_launch_update(m, m->d_x, m->d_f, 1);
         CUDA_CHECK(cudaMemsetAsync(m->d_F, 0, (size_t)m->ndofs * sizeof(double), m->stream));
         amaru_nodes_to_eq(m, m->d_f, m->d_F, 0);
+        if (m->nranks > 1) amaru_allreduce_sum(m, m->d_F, m->ndofs);   // every rank contributes the rows it owns
         CUDA_CHECK(cudaMemcpyAsync(Fin, m->d_F, (size_t)m->ndofs * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
         CUDA_CHECK(cudaStreamSynchronize(m->stream));
         return AMARU_OK;
@@ -614,6 +726,7 @@ int amaru_internal_forces(amaru_model *m, double *Fin, char *msg, int msglen) {
 int amaru_matvec(amaru_model *m, double a, double b, const double *x, double *y, char *msg, int msglen) {
     return guarded(msg, msglen, [&]() {
         AMARU_REQUIRE(m && x && y, AMARU_ERR_ARG, "null argument");
+        if (m->grp) return amaru_group_product(m, 0, a, b, x, y, 0, nullptr, msg, msglen);
         use_device(m);
         AMARU_REQUIRE(b == 0.0 || m->d_M != nullptr, AMARU_ERR_ARG, "amaru_matvec: mass matrix not assembled");
         // y = a*(K x) + b*(M x): two products on the stored matrices, no combined matrix is formed
@@ -640,6 +753,7 @@ int amaru_matvec(amaru_model *m, double a, double b, const double *x, double *y,
 int amaru_operator_apply(amaru_model *m, const double *x, double *y, int masked, double *pAp, char *msg, int msglen) {
     return guarded(msg, msglen, [&]() {
         AMARU_REQUIRE(m && x && y, AMARU_ERR_ARG, "null argument");
+        if (m->grp) return amaru_group_product(m, 1, 0, 0, x, y, masked, pAp, msg, msglen);
         use_device(m);
         const size_t bytes = (size_t)m->ndofs * sizeof(double);
         CUDA_CHECK(cudaMemcpyAsync(m->d_U, x, bytes, cudaMemcpyHostToDevice, m->stream));
@@ -658,6 +772,7 @@ int amaru_operator_apply(amaru_model *m, const double *x, double *y, int masked,
 int amaru_set_device_vectors(amaru_model *m, const double *U, const double *F, char *msg, int msglen) {
     return guarded(msg, msglen, [&]() {
         AMARU_REQUIRE(m && U && F, AMARU_ERR_ARG, "null argument");
+        if (m->grp) return amaru_group_set_device_vectors(m, U, F, msg, msglen);
         use_device(m);
         const size_t bytes = (size_t)m->ndofs * sizeof(double);
         if (!m->d_U0) CUDA_CHECK(cudaMalloc(&m->d_U0, bytes));
@@ -672,14 +787,16 @@ int amaru_set_device_vectors(amaru_model *m, const double *U, const double *F, c
 int amaru_newton_iteration_device(amaru_model *m, double cg_rtol, int cg_maxit, int precond, double *phase_ms, int *iters,
                                   double *relres, char *msg, int msglen) {
     return guarded(msg, msglen, [&]() {
+        if (m && m->grp) return amaru_group_newton_iteration(m, cg_rtol, cg_maxit, precond, phase_ms, iters, relres, msg, msglen);
         AMARU_REQUIRE(m && m->d_U0 && m->d_F0, AMARU_ERR_ARG, "amaru_newton_iteration_device: call amaru_set_device_vectors first");
         use_device(m);
         const size_t bytes = (size_t)m->ndofs * sizeof(double);
-        cudaEvent_t ev[4];
-        for (auto &e : ev) CUDA_CHECK(cudaEventCreate(&e));
+        EventSet<4> evs;
+        cudaEvent_t *ev = evs.ev;
         CUDA_CHECK(cudaEventRecord(ev[0], m->stream));
         reset_status(m);
         amaru_launch_assemble(m, 0);                                   // mount_K            (mech-solver.jl:327)
+        m->blended = false;
         amaru_combine_matrix(m);
         amaru_ebe_refresh(m);
         if (m->nranks > 1) amaru_allreduce_max_int(m, m->d_status);
@@ -703,7 +820,6 @@ int amaru_newton_iteration_device(amaru_model *m, double cg_rtol, int cg_maxit, 
             CUDA_CHECK(cudaEventElapsedTime(&t, ev[0], ev[3]));
             phase_ms[3] = t;
         }
-        for (auto &e : ev) cudaEventDestroy(e);
         if (iters) *iters = info.iters;
         if (relres) *relres = info.relres;
         if (as) st = as;
@@ -716,10 +832,10 @@ int amaru_newton_iteration_device(amaru_model *m, double cg_rtol, int cg_maxit, 
 int amaru_time_kernel(amaru_model *m, int kind, int precond, int reps, double *avg_ms, char *msg, int msglen) {
     return guarded(msg, msglen, [&]() {
         AMARU_REQUIRE(m && avg_ms && reps > 0, AMARU_ERR_ARG, "bad argument");
+        AMARU_REQUIRE(!m->grp, AMARU_ERR_UNSUPPORTED, "amaru_time_kernel: single-GPU handles only");
         use_device(m);
-        cudaEvent_t e0, e1;
-        CUDA_CHECK(cudaEventCreate(&e0));
-        CUDA_CHECK(cudaEventCreate(&e1));
+        EventSet<2> evs;
+        cudaEvent_t e0 = evs.ev[0], e1 = evs.ev[1];
         if (kind >= 3 || kind == 0) amaru_time_cg_kernel(m, kind, precond, 1);   // warm-up
         CUDA_CHECK(cudaEventRecord(e0, m->stream));
         if (kind == 1) {
@@ -734,20 +850,20 @@ int amaru_time_kernel(amaru_model *m, int kind, int precond, int reps, double *a
         float t = 0.f;
         CUDA_CHECK(cudaEventElapsedTime(&t, e0, e1));
         *avg_ms = (double)t / reps;
-        cudaEventDestroy(e0);
-        cudaEventDestroy(e1);
         return AMARU_OK;
     });
 }
 
 int amaru_set_operator(amaru_model *m, int kind) {
     if (!m || (kind != AMARU_OPERATOR_CSR && kind != AMARU_OPERATOR_EBE)) return AMARU_ERR_ARG;
+    if (m->grp) return amaru_group_simple(m, 4, kind, 0, nullptr, 0);
     m->op_ebe = kind == AMARU_OPERATOR_EBE;
     return AMARU_OK;
 }
 
 int amaru_set_profiling(amaru_model *m, int on) {
     if (!m) return AMARU_ERR_ARG;
+    if (m->grp) return amaru_group_simple(m, 5, on, 0, nullptr, 0);
     m->profiling = on != 0;
     m->prof_spmv_ms = 0.0;
     m->prof_spmv_n = 0;
@@ -756,9 +872,17 @@ int amaru_set_profiling(amaru_model *m, int on) {
 
 int amaru_get_profile(amaru_model *m, double *spmv_ms_total, int64_t *spmv_launches) {
     if (!m) return AMARU_ERR_ARG;
+    if (m->grp) m = amaru_group_part(m, 0);
     if (spmv_ms_total) *spmv_ms_total = m->prof_spmv_ms;
     if (spmv_launches) *spmv_launches = m->prof_spmv_n;
     return AMARU_OK;
+}
+
+int amaru_comm_selftest(amaru_model *m, int skip_rank, char *msg, int msglen) {
+    return guarded(msg, msglen, [&]() {
+        AMARU_REQUIRE(m && m->grp, AMARU_ERR_UNSUPPORTED, "amaru_comm_selftest: multi-GPU handles (ngpus > 1) only");
+        return amaru_group_comm_selftest(m, skip_rank, msg, msglen);
+    });
 }
 
 }  // extern "C"

@@ -143,6 +143,9 @@ struct amaru_model {
     // multi-GPU
     int rank = 0, nranks = 1;
     void *comm = nullptr;          // HaloComm* (halo.cu)
+    struct AmaruGroup *grp = nullptr;     // != nullptr: this handle is a group of per-GPU parts in one process (group.cu)
+    struct AmaruGroup *grp_of = nullptr;  // != nullptr: this handle is a part of that group
+    bool io_shared = false;        // part of a group: d_U / d_F / d_U0 / d_F0 alias the first part's vectors (peer access)
 
     // output side (recovery.cu)
     void *recovery = nullptr;      // Recovery*
@@ -150,6 +153,8 @@ struct amaru_model {
 
     // matrix-free tangent operator of the CG loop (ebe.cu)
     void *ebe = nullptr;           // Ebe*
+    double *d_Ksave = nullptr;     // K of the predictor step (amaru_tangent_save) for K = a1*K + a2*K2 of the ME / Ralston schemes
+    bool blended = false;          // d_K holds such a blend: the per-IP tangent data no longer describes it -> CSR products
     bool op_ebe = true;            // CG products: element-by-element (default) or block-CSR SpMV (AMARU_OPERATOR=csr)
 
     bool cg_graph = true;          // replay the CG batches as a CUDA graph on one GPU (AMARU_CG_GRAPH=0 disables)
@@ -165,6 +170,53 @@ struct amaru_model {
     std::vector<int32_t> h_rowptr, h_col, h_eqid;
     std::vector<uint8_t> h_fixed;
 };
+
+// ---- internals of abi.cu shared with group.cu ------------------------------------------------------------------
+struct CreateArgs {
+    int ndim, stressmodel;
+    double thickness;
+    int64_t nnodes, nowned;
+    const double *coords;
+    int nbatches;
+    const int32_t *batch_shape;
+    const int64_t *batch_nelem;
+    const int32_t *conn;
+    const int32_t *elem_mat;
+    int nmats;
+    const int32_t *mat_kind;
+    const double *mat_params;
+    const int32_t *eqid;
+    const uint8_t *prescribed;   // optional (partitioned); else eqid >= nu
+    int64_t ndofs, nu;
+    int device;
+    int rank, nranks;
+};
+struct SolveInfo;
+amaru_model *amaru_create_impl(const CreateArgs &a);
+void amaru_free_model(amaru_model *m);
+int amaru_solve_device(amaru_model *m, double cg_rtol, int cg_maxit, int precond, SolveInfo &info);
+int amaru_update_device(amaru_model *m);
+const char *amaru_status_text(int st);
+int amaru_read_status(amaru_model *m);
+void amaru_reset_status(amaru_model *m);
+void amaru_set_element_ownership(amaru_model *m, const int32_t *conn, int nneigh, const int32_t *neigh_rank,
+                                 const int64_t *recv_start, const int64_t *recv_count);
+// group.cu: multi-GPU handle of one process (h->grp != nullptr)
+void amaru_group_barrier(amaru_model *part);   // stream sync + host barrier over the parts (throws if a part failed)
+int amaru_group_create(const CreateArgs &a, int ngpus, const int32_t *devices, int partitioner, amaru_model **out, char *msg, int msglen);
+int amaru_group_destroy(amaru_model *h);
+int64_t amaru_group_sum(const amaru_model *h, int what /*0 blocks, 1 launches, 2 colours*/);
+amaru_model *amaru_group_part(const amaru_model *h, int r);
+int amaru_group_state(amaru_model *h, bool set, double *sigma, double *eps, double *epa, double *dlam, char *msg, int msglen);
+int amaru_group_simple(amaru_model *h, int what /*0 backup 1 restore 2 assemble_K 3 system matrix 4 operator 5 profiling 6 tangent_save 7 tangent_blend*/, double a, double b, char *msg, int msglen);
+int amaru_group_assemble_M(amaru_model *h, const double *rho, char *msg, int msglen);
+int amaru_group_solve(amaru_model *h, double *U, double *F, double cg_rtol, int cg_maxit, int precond, int *iters, double *relres, char *msg, int msglen);
+int amaru_group_update(amaru_model *h, const double *dU, double *dFin, int mode, char *msg, int msglen);
+int amaru_group_product(amaru_model *h, int what, double a, double b, const double *x, double *y, int masked, double *pAp, char *msg, int msglen);
+int amaru_group_set_device_vectors(amaru_model *h, const double *U, const double *F, char *msg, int msglen);
+int amaru_group_newton_iteration(amaru_model *h, double cg_rtol, int cg_maxit, int precond, double *phase_ms, int *iters, double *relres, char *msg, int msglen);
+int amaru_group_comm_selftest(amaru_model *h, int skip_rank, char *msg, int msglen);
+void amaru_group_refresh_output_state(amaru_model *h);   // wrapper's IP state planes <- owners' copies (before recovery)
 
 // ---- kernels' host entry points (one per .cu) -----------------------------------------------------------------
 void amaru_build_map(amaru_model *m, Batch &b);                     // assemble.cu
@@ -213,4 +265,7 @@ void amaru_allreduce_max_int(amaru_model *m, int *d_val);
 void amaru_comm_setup(amaru_model *m, int nneigh, const int32_t *neigh_rank, const int64_t *send_ptr,
                       const int32_t *send_nodes, const int64_t *recv_start, const int64_t *recv_count, const void *uid);
 void amaru_comm_destroy(amaru_model *m);
+bool amaru_comm_is_p2p(const amaru_model *m);                        // CG-loop exchanges run as peer-memory kernels
+void amaru_comm_check(amaru_model *m);                               // throws AMARU_ERR_COMM if a peer-memory wait timed out
+void amaru_p2p_connect_direct(amaru_model *const *parts, int n);    // in-process peers (amaru_create with ngpus > 1)
 void amaru_recovery_destroy(amaru_model *m);   // recovery.cu

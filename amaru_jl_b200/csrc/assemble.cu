@@ -12,6 +12,8 @@
 // Determinism without atomics: elements are processed colour by colour (elements of one colour share no node, hence
 // no destination block), one launch per colour, so every block receives its contributions in a fixed order.
 // K3 (consistent mass, mech-solid.jl:169-205 + dyn-solver.jl:72-103) uses the same map with N_a·N_b·I blocks.
+#include <atomic>
+
 #include "materials.cuh"
 
 namespace {
@@ -262,11 +264,13 @@ template <int NN, int ND, int NIP, int EPB, int NT>
 void launch_K(amaru_model *m, Batch &b) {
     using L = AsmSmem<NN, ND, NIP, EPB>;
     const size_t smem = L::doubles * sizeof(double);
-    static bool attr_set = false;
-    if (!attr_set) {
+    // function attributes are per device (multi-GPU handles drive several devices from one process): one bit per ordinal
+    static std::atomic<uint64_t> attr_set{0};
+    const uint64_t bit = 1ull << (m->device & 63);
+    if (!(attr_set.load(std::memory_order_acquire) & bit)) {
         CUDA_CHECK(cudaFuncSetAttribute(k_assemble_K<NN, ND, NIP, EPB, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)smem));
-        attr_set = true;
+        attr_set.fetch_or(bit, std::memory_order_release);
     }
     AsmArgs a;
     a.coords = m->d_coords; a.conn = b.d_conn; a.emat = b.d_emat; a.map = b.d_map;

@@ -9,6 +9,9 @@
 #include <dlfcn.h>
 #include <nccl.h>
 
+#include <algorithm>
+#include <cstddef>
+#include <cstdlib>
 #include <cstring>
 
 #include "amaru_internal.h"
@@ -73,11 +76,13 @@ struct HaloComm {
     void *peer_win[16] = {nullptr};        // every rank's window (own entry = d_win)
     std::vector<void *> opened;            // cudaIpcOpenMemHandle results to close
     double **d_peer_p = nullptr;           // [nneigh] neighbours' p vectors
+    double **d_peer_x = nullptr;           // [nneigh] neighbours' x vectors
+    bool direct = false;                   // peers are devices of this process (no NCCL communicator, no cudaIpc)
+    unsigned long long timeout_ns = 10000000000ull;
     int64_t *d_peer_start = nullptr;       // [nneigh] where this rank's nodes start in the neighbour's numbering
     int64_t *d_send_ptr = nullptr;
     int *d_neigh = nullptr;
     unsigned int *d_counter = nullptr;
-    unsigned long long halo_epoch = 0, scal_epoch = 0;
 };
 
 __global__ void k_pack(int64_t n, int nd, const int32_t *__restrict__ nodes, const double *__restrict__ v, double *buf) {
@@ -89,26 +94,32 @@ __global__ void k_pack(int64_t n, int nd, const int32_t *__restrict__ nodes, con
 }
 
 
-// ---- peer-memory path (AMARU_P2P, opt-in): the per-iteration exchanges of the CG loop without NCCL ------------------
-// Every rank exports (cudaIpc) a small window {scalar slots, flags} and its p vector; after amaru_p2p_connect a rank holds
-// device pointers into every peer's window and into its neighbours' p.  Two kernels replace the three NCCL calls of an
-// iteration:
-//   k_p2p_halo       stores the boundary entries of p straight into the neighbours' ghost slots over NVLink, then (last
-//                    block) raises its epoch flag in each neighbour's window and waits for the neighbours' flags;
-//   k_p2p_allreduce  one warp: lane r stores this rank's partial dots into rank r's window (slot of this rank, buffer
-//                    epoch&1) and raises the flag, then the warp waits for all ranks' flags in its own window and sums the
-//                    slots in rank order — every rank forms bitwise the same sum.
-// Safety of the reuse: a slot/flag of parity e&1 is rewritten at epoch e+2, which a rank can only reach after it finished
-// epoch e+1, i.e. after every peer entered epoch e+1, i.e. after every peer finished reading epoch e.  Ghost entries of p
-// are rewritten only after an all-reduce that every rank enters after its SpMV of the previous iteration.
+// ---- peer-memory path: the per-iteration exchanges of the CG loop without NCCL ----------------------------------------
+// Every rank owns a small window {scalar slots, flags, epochs, abort flag} and lets its peers address it and its p / x
+// vectors (cudaIpc handles between processes, plain peer access inside one process).  Two kernels replace the three NCCL
+// calls of an iteration:
+//   k_p2p_halo       stores the boundary entries of a vector straight into the neighbours' ghost slots over NVLink, then
+//                    (last block) raises its epoch flag in each neighbour's window and waits for the neighbours' flags;
+//   k_p2p_allreduce  one warp: lane r stores this rank's partial values into rank r's window (slot of this rank, buffer
+//                    epoch&1) and raises the flag, then the warp waits for all ranks' flags in its own window and combines
+//                    the slots in rank order — every rank forms bitwise the same sum / max.
+// Epochs live in the window and are advanced by the kernels themselves, so a batch of CG iterations is a fixed launch
+// sequence and can be replayed as a CUDA graph.  Safety of the reuse: a slot/flag of parity e&1 is rewritten at epoch e+2,
+// which a rank can only reach after it finished epoch e+1, i.e. after every peer entered epoch e+1, i.e. after every peer
+// finished reading epoch e.  Ghost entries are rewritten only after an all-reduce that every rank enters after the
+// product that read them.  Every wait is bounded (timeout_ns of %globaltimer): a rank that gives up raises the abort flag
+// in every window, all spinning kernels leave, later ones return at once, and the host reports AMARU_ERR_COMM.
 constexpr int P2P_MAXR = 16;
 struct P2PWin {
     double slot[2][P2P_MAXR][4];
     unsigned long long sflag[2][P2P_MAXR];
     unsigned long long hflag[P2P_MAXR];
+    unsigned long long halo_epoch, scal_epoch;   // completed epochs of this rank
+    int abort;
 };
 struct P2PDev {
     int rank, nranks;
+    unsigned long long timeout_ns;
     P2PWin *win[P2P_MAXR];
 };
 
@@ -120,9 +131,36 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
     asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// wait until *flag >= epoch; false (and the abort flag raised everywhere) when the budget ran out or a peer aborted
+__device__ bool p2p_wait(const P2PDev &pd, const unsigned long long *flag, unsigned long long epoch) {
+    P2PWin *me = pd.win[pd.rank];
+    const unsigned long long t0 = global_ns();
+    unsigned int it = 0;
+    while (ld_acquire_sys(flag) < epoch) {
+        if ((++it & 255u) == 0) {
+            const bool late = global_ns() - t0 > pd.timeout_ns;
+            if (late || *reinterpret_cast<volatile int *>(&me->abort)) {
+                for (int r = 0; r < pd.nranks; r++) *reinterpret_cast<volatile int *>(&pd.win[r]->abort) = 1;
+                __threadfence_system();
+                return false;
+            }
+        }
+        __nanosleep(20);
+    }
+    return true;
+}
 
-__global__ void k_p2p_allreduce(P2PDev pd, unsigned long long epoch, double *vals, int n) {
+// op 0: sum, 1: max
+__global__ void k_p2p_allreduce(P2PDev pd, double *vals, int n, int op) {
     const int lane = threadIdx.x;
+    P2PWin *me = pd.win[pd.rank];
+    if (*reinterpret_cast<volatile int *>(&me->abort)) return;
+    const unsigned long long epoch = me->scal_epoch + 1;
     const int par = (int)(epoch & 1ull);
     if (lane < pd.nranks) {
         P2PWin *w = pd.win[lane];
@@ -130,49 +168,69 @@ __global__ void k_p2p_allreduce(P2PDev pd, unsigned long long epoch, double *val
         __threadfence_system();
         st_release_sys(&w->sflag[par][pd.rank], epoch);
     }
-    P2PWin *me = pd.win[pd.rank];
-    if (lane < pd.nranks)
-        while (ld_acquire_sys(&me->sflag[par][lane]) < epoch) __nanosleep(20);
-    __syncwarp();
+    bool ok = true;
+    if (lane < pd.nranks) ok = p2p_wait(pd, &me->sflag[par][lane], epoch);
+    ok = __all_sync(0xffffffffu, ok);
     if (lane == 0) {
-        for (int k = 0; k < n; k++) {
-            double s = 0.0;
-            for (int r = 0; r < pd.nranks; r++) s += *reinterpret_cast<volatile double *>(&me->slot[par][r][k]);
-            vals[k] = s;
+        if (ok) {
+            for (int k = 0; k < n; k++) {
+                double s = *reinterpret_cast<volatile double *>(&me->slot[par][0][k]);
+                for (int r = 1; r < pd.nranks; r++) {
+                    const double v = *reinterpret_cast<volatile double *>(&me->slot[par][r][k]);
+                    s = op == 0 ? s + v : fmax(s, v);
+                }
+                vals[k] = s;
+            }
         }
+        me->scal_epoch = epoch;
     }
 }
 
-__global__ void k_p2p_halo(P2PDev pd, unsigned long long epoch, int nneigh, const int *__restrict__ neigh,
-                           const int64_t *__restrict__ send_ptr, const int32_t *__restrict__ send_nodes,
-                           double *const *__restrict__ peer_p, const int64_t *__restrict__ peer_start, int nd,
-                           const double *__restrict__ v, unsigned int *counter) {
+__global__ void k_p2p_halo(P2PDev pd, int nneigh, const int *__restrict__ neigh, const int64_t *__restrict__ send_ptr,
+                           const int32_t *__restrict__ send_nodes, double *const *__restrict__ peer_v,
+                           const int64_t *__restrict__ peer_start, int nd, const double *__restrict__ v, unsigned int *counter) {
     __shared__ bool last;
+    P2PWin *me = pd.win[pd.rank];
+    if (*reinterpret_cast<volatile int *>(&me->abort)) return;
+    const unsigned long long epoch = *reinterpret_cast<volatile unsigned long long *>(&me->halo_epoch) + 1;
     const int64_t total = send_ptr[nneigh] * nd;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t k = i / nd;
         const int d = (int)(i - k * nd);
         int q = 0;
         while (k >= send_ptr[q + 1]) q++;
-        peer_p[q][(peer_start[q] + (k - send_ptr[q])) * nd + d] = v[(int64_t)send_nodes[k] * nd + d];
+        peer_v[q][(peer_start[q] + (k - send_ptr[q])) * nd + d] = v[(int64_t)send_nodes[k] * nd + d];
     }
     __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) last = atomicInc(counter, gridDim.x - 1) == gridDim.x - 1;
     __syncthreads();
-    if (last && threadIdx.x < nneigh) {
-        __threadfence_system();   // the other blocks' remote stores (fenced before their counter increment) precede the flag
-        st_release_sys(&pd.win[neigh[threadIdx.x]]->hflag[pd.rank], epoch);
-        const unsigned long long *mine = &pd.win[pd.rank]->hflag[neigh[threadIdx.x]];
-        while (ld_acquire_sys(mine) < epoch) __nanosleep(20);
+    if (last) {   // every block has read the epoch and fenced its remote stores before its counter increment
+        if (threadIdx.x < nneigh) {
+            __threadfence_system();
+            st_release_sys(&pd.win[neigh[threadIdx.x]]->hflag[pd.rank], epoch);
+            p2p_wait(pd, &me->hflag[neigh[threadIdx.x]], epoch);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) me->halo_epoch = epoch;
     }
 }
 
 }  // namespace
 
+static P2PDev make_pd(amaru_model *m, HaloComm *hc) {
+    P2PDev pd;
+    pd.rank = m->rank;
+    pd.nranks = m->nranks;
+    pd.timeout_ns = hc->timeout_ns;
+    for (int r = 0; r < P2P_MAXR; r++) pd.win[r] = static_cast<P2PWin *>(r < m->nranks ? hc->peer_win[r] : nullptr);
+    return pd;
+}
+
+// `uid` == nullptr: peers are devices of this process (amaru_create with ngpus > 1): no NCCL communicator is made, every
+// exchange goes through peer memory once amaru_p2p_connect_direct has run
 void amaru_comm_setup(amaru_model *m, int nneigh, const int32_t *neigh_rank, const int64_t *send_ptr,
                       const int32_t *send_nodes, const int64_t *recv_start, const int64_t *recv_count, const void *uid) {
-    NcclApi &api = nccl();
     HaloComm *hc = new HaloComm();
     m->comm = hc;
     hc->nneigh = nneigh;
@@ -181,6 +239,7 @@ void amaru_comm_setup(amaru_model *m, int nneigh, const int32_t *neigh_rank, con
     hc->recv_start.assign(recv_start, recv_start + nneigh);
     hc->recv_count.assign(recv_count, recv_count + nneigh);
     hc->nsend = send_ptr[nneigh];
+    if (const char *e = getenv("AMARU_P2P_TIMEOUT_MS")) hc->timeout_ns = (unsigned long long)std::max(1, atoi(e)) * 1000000ull;
     for (int q = 0; q < nneigh; q++) {
         AMARU_REQUIRE(neigh_rank[q] >= 0 && neigh_rank[q] < m->nranks && neigh_rank[q] != m->rank, AMARU_ERR_ARG, "bad neighbour rank");
         AMARU_REQUIRE(recv_start[q] >= m->nowned && recv_start[q] + recv_count[q] <= m->nnodes, AMARU_ERR_ARG, "bad ghost range");
@@ -190,9 +249,13 @@ void amaru_comm_setup(amaru_model *m, int nneigh, const int32_t *neigh_rank, con
     CUDA_CHECK(cudaMalloc(&hc->d_send_nodes, std::max<int64_t>(hc->nsend, 1) * sizeof(int32_t)));
     CUDA_CHECK(cudaMemcpy(hc->d_send_nodes, send_nodes, hc->nsend * sizeof(int32_t), cudaMemcpyHostToDevice));
     CUDA_CHECK(cudaMalloc(&hc->d_sendbuf, std::max<int64_t>(hc->nsend, 1) * m->nd * sizeof(double)));
-    ncclUniqueId id;
-    std::memcpy(&id, uid, sizeof(id));
-    NCCL_CHECK(api.CommInitRank(&hc->comm, m->nranks, id, m->rank));
+    if (uid) {
+        ncclUniqueId id;
+        std::memcpy(&id, uid, sizeof(id));
+        NCCL_CHECK(nccl().CommInitRank(&hc->comm, m->nranks, id, m->rank));
+    } else {
+        hc->direct = true;
+    }
 }
 
 void amaru_comm_destroy(amaru_model *m) {
@@ -202,6 +265,7 @@ void amaru_comm_destroy(amaru_model *m) {
     for (void *p : hc->opened) cudaIpcCloseMemHandle(p);
     cudaFree(hc->d_win);
     cudaFree(hc->d_peer_p);
+    cudaFree(hc->d_peer_x);
     cudaFree(hc->d_peer_start);
     cudaFree(hc->d_send_ptr);
     cudaFree(hc->d_neigh);
@@ -212,24 +276,37 @@ void amaru_comm_destroy(amaru_model *m) {
     m->comm = nullptr;
 }
 
+bool amaru_comm_is_p2p(const amaru_model *m) {
+    const HaloComm *hc = static_cast<const HaloComm *>(m->comm);
+    return hc && hc->p2p;
+}
+
+// after a batch of peer-memory kernels: did any rank give up waiting?
+void amaru_comm_check(amaru_model *m) {
+    HaloComm *hc = static_cast<HaloComm *>(m->comm);
+    if (!hc || !hc->p2p || !hc->d_win) return;
+    int ab = 0;
+    CUDA_CHECK(cudaMemcpyAsync(&ab, reinterpret_cast<char *>(hc->d_win) + offsetof(P2PWin, abort), sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+    CUDA_CHECK(cudaStreamSynchronize(m->stream));
+    if (ab) throw AmaruError{AMARU_ERR_COMM, "peer-memory exchange timed out: a rank left the collective sequence"};
+}
+
 // ghost entries of the node-major vector d_v <- owners' values
 void amaru_halo_exchange(amaru_model *m, double *d_v) {
     if (m->nranks <= 1) return;
     HaloComm *hc = static_cast<HaloComm *>(m->comm);
-    AMARU_REQUIRE(hc && hc->comm, AMARU_ERR_COMM, "halo exchange: communicator not initialised");
-    if (hc->p2p && d_v == m->d_p) {   // CG loop: push into the neighbours' ghost slots, flag, wait (no NCCL)
-        P2PDev pd;
-        pd.rank = m->rank;
-        pd.nranks = m->nranks;
-        for (int r = 0; r < P2P_MAXR; r++) pd.win[r] = static_cast<P2PWin *>(r < m->nranks ? hc->peer_win[r] : nullptr);
+    AMARU_REQUIRE(hc && (hc->comm || hc->direct), AMARU_ERR_COMM, "halo exchange: communicator not initialised");
+    double **peer = d_v == m->d_p ? hc->d_peer_p : (d_v == m->d_x ? hc->d_peer_x : nullptr);
+    if (hc->p2p && peer) {   // push into the neighbours' ghost slots, flag, wait (no NCCL)
         const int64_t n = hc->nsend * m->nd;
         const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, (int64_t)m->nsm * 2));
-        k_p2p_halo<<<blocks, 256, 0, m->stream>>>(pd, ++hc->halo_epoch, hc->nneigh, hc->d_neigh, hc->d_send_ptr, hc->d_send_nodes,
-                                                  hc->d_peer_p, hc->d_peer_start, m->nd, d_v, hc->d_counter);
+        k_p2p_halo<<<blocks, 256, 0, m->stream>>>(make_pd(m, hc), hc->nneigh, hc->d_neigh, hc->d_send_ptr, hc->d_send_nodes, peer,
+                                                  hc->d_peer_start, m->nd, d_v, hc->d_counter);
         m->launches++;
         CUDA_CHECK(cudaGetLastError());
         return;
     }
+    AMARU_REQUIRE(hc->comm != nullptr, AMARU_ERR_COMM, "halo exchange: vector has no peer mapping and there is no NCCL communicator");
     NcclApi &api = nccl();
     if (hc->nsend > 0) {
         const int64_t n = hc->nsend * m->nd;
@@ -246,34 +323,34 @@ void amaru_halo_exchange(amaru_model *m, double *d_v) {
     NCCL_CHECK(api.GroupEnd());
 }
 
-void amaru_allreduce_sum(amaru_model *m, double *d_vals, int64_t n) {
-    if (m->nranks <= 1) return;
+static void small_allreduce(amaru_model *m, double *d_vals, int64_t n, int op) {
     HaloComm *hc = static_cast<HaloComm *>(m->comm);
-    AMARU_REQUIRE(hc && hc->comm, AMARU_ERR_COMM, "all-reduce: communicator not initialised");
+    AMARU_REQUIRE(hc && (hc->comm || hc->direct), AMARU_ERR_COMM, "all-reduce: communicator not initialised");
     if (hc->p2p && n <= 4) {   // the scalar all-reduces of the CG loop through peer memory
-        P2PDev pd;
-        pd.rank = m->rank;
-        pd.nranks = m->nranks;
-        for (int r = 0; r < P2P_MAXR; r++) pd.win[r] = static_cast<P2PWin *>(r < m->nranks ? hc->peer_win[r] : nullptr);
-        k_p2p_allreduce<<<1, 32, 0, m->stream>>>(pd, ++hc->scal_epoch, d_vals, (int)n);
+        k_p2p_allreduce<<<1, 32, 0, m->stream>>>(make_pd(m, hc), d_vals, (int)n, op);
         m->launches++;
         CUDA_CHECK(cudaGetLastError());
         return;
     }
-    NCCL_CHECK(nccl().AllReduce(d_vals, d_vals, (size_t)n, ncclDouble, ncclSum, hc->comm, m->stream));
+    AMARU_REQUIRE(hc->comm != nullptr, AMARU_ERR_COMM, "all-reduce of a long vector needs the NCCL communicator");
+    NCCL_CHECK(nccl().AllReduce(d_vals, d_vals, (size_t)n, ncclDouble, op == 0 ? ncclSum : ncclMax, hc->comm, m->stream));
+}
+
+void amaru_allreduce_sum(amaru_model *m, double *d_vals, int64_t n) {
+    if (m->nranks <= 1) return;
+    small_allreduce(m, d_vals, n, 0);
 }
 
 void amaru_allreduce_max(amaru_model *m, double *d_vals, int64_t n) {
     if (m->nranks <= 1) return;
-    HaloComm *hc = static_cast<HaloComm *>(m->comm);
-    AMARU_REQUIRE(hc && hc->comm, AMARU_ERR_COMM, "all-reduce: communicator not initialised");
-    NCCL_CHECK(nccl().AllReduce(d_vals, d_vals, (size_t)n, ncclDouble, ncclMax, hc->comm, m->stream));
+    small_allreduce(m, d_vals, n, 1);
 }
 
 void amaru_allreduce_max_int(amaru_model *m, int *d_val) {
     if (m->nranks <= 1) return;
     HaloComm *hc = static_cast<HaloComm *>(m->comm);
-    AMARU_REQUIRE(hc && hc->comm, AMARU_ERR_COMM, "all-reduce: communicator not initialised");
+    AMARU_REQUIRE(hc && (hc->comm || hc->direct), AMARU_ERR_COMM, "all-reduce: communicator not initialised");
+    if (hc->direct) return;   // one process: the caller combines the ranks' status words on the host
     NCCL_CHECK(nccl().AllReduce(d_val, d_val, 1, ncclInt, ncclMax, hc->comm, m->stream));
 }
 
@@ -291,7 +368,65 @@ extern "C" int amaru_nccl_unique_id(void *uid128, char *msg, int msglen) {
     }
 }
 
-// ---- peer-memory path: handle exchange (the host all-gathers the 128-byte records, e.g. with torch.distributed / MPI.jl)
+static void ensure_window(amaru_model *m, HaloComm *hc) {
+    if (!hc->d_win) {
+        CUDA_CHECK(cudaMalloc(&hc->d_win, sizeof(P2PWin)));
+        CUDA_CHECK(cudaMemset(hc->d_win, 0, sizeof(P2PWin)));
+    }
+}
+
+// device-side tables of the push kernel: neighbours' vectors, where this rank's nodes start in their numbering
+static void upload_peer_tables(amaru_model *m, HaloComm *hc, const std::vector<double *> &peer_p, const std::vector<double *> &peer_x,
+                               const int64_t *peer_recv_start) {
+    const size_t nn = (size_t)std::max(hc->nneigh, 1);
+    CUDA_CHECK(cudaMalloc(&hc->d_peer_p, nn * sizeof(double *)));
+    CUDA_CHECK(cudaMalloc(&hc->d_peer_start, nn * sizeof(int64_t)));
+    CUDA_CHECK(cudaMalloc(&hc->d_send_ptr, (nn + 1) * sizeof(int64_t)));
+    CUDA_CHECK(cudaMalloc(&hc->d_neigh, nn * sizeof(int)));
+    CUDA_CHECK(cudaMalloc(&hc->d_counter, sizeof(unsigned int)));
+    CUDA_CHECK(cudaMemset(hc->d_counter, 0, sizeof(unsigned int)));
+    CUDA_CHECK(cudaMemcpy(hc->d_peer_p, peer_p.data(), hc->nneigh * sizeof(double *), cudaMemcpyHostToDevice));
+    if (!peer_x.empty()) {
+        CUDA_CHECK(cudaMalloc(&hc->d_peer_x, nn * sizeof(double *)));
+        CUDA_CHECK(cudaMemcpy(hc->d_peer_x, peer_x.data(), hc->nneigh * sizeof(double *), cudaMemcpyHostToDevice));
+    }
+    if (hc->nneigh) CUDA_CHECK(cudaMemcpy(hc->d_peer_start, peer_recv_start, hc->nneigh * sizeof(int64_t), cudaMemcpyHostToDevice));
+    CUDA_CHECK(cudaMemcpy(hc->d_send_ptr, hc->send_ptr.data(), (hc->nneigh + 1) * sizeof(int64_t), cudaMemcpyHostToDevice));
+    if (hc->nneigh) CUDA_CHECK(cudaMemcpy(hc->d_neigh, hc->neigh.data(), hc->nneigh * sizeof(int), cudaMemcpyHostToDevice));
+    CUDA_CHECK(cudaDeviceSynchronize());
+    hc->p2p_ready = true;
+}
+
+// ---- in-process variant (amaru_create with ngpus > 1): the parts are devices of this process with peer access enabled;
+// called once, from one thread, after every part's amaru_comm_setup(uid = nullptr)
+void amaru_p2p_connect_direct(amaru_model *const *parts, int n) {
+    AMARU_REQUIRE(n > 1 && n <= P2P_MAXR, AMARU_ERR_ARG, "peer-memory path: 2..16 GPUs");
+    for (int r = 0; r < n; r++) {
+        CUDA_CHECK(cudaSetDevice(parts[r]->device));
+        ensure_window(parts[r], static_cast<HaloComm *>(parts[r]->comm));
+    }
+    for (int r = 0; r < n; r++) {
+        amaru_model *m = parts[r];
+        HaloComm *hc = static_cast<HaloComm *>(m->comm);
+        CUDA_CHECK(cudaSetDevice(m->device));
+        for (int q = 0; q < n; q++) hc->peer_win[q] = static_cast<HaloComm *>(parts[q]->comm)->d_win;
+        std::vector<double *> pp((size_t)std::max(hc->nneigh, 1), nullptr), px((size_t)std::max(hc->nneigh, 1), nullptr);
+        std::vector<int64_t> pstart((size_t)std::max(hc->nneigh, 1), 0);
+        for (int i = 0; i < hc->nneigh; i++) {
+            amaru_model *mq = parts[hc->neigh[(size_t)i]];
+            HaloComm *hq = static_cast<HaloComm *>(mq->comm);
+            pp[(size_t)i] = mq->d_p;
+            px[(size_t)i] = mq->d_x;
+            const auto it = std::find(hq->neigh.begin(), hq->neigh.end(), r);
+            AMARU_REQUIRE(it != hq->neigh.end(), AMARU_ERR_ARG, "halo lists are not symmetric");
+            pstart[(size_t)i] = hq->recv_start[(size_t)(it - hq->neigh.begin())];
+        }
+        upload_peer_tables(m, hc, pp, px, pstart.data());
+        hc->p2p = true;
+    }
+}
+
+// ---- between processes: handle exchange (the host all-gathers the 128-byte records, e.g. with torch.distributed / MPI.jl)
 extern "C" int amaru_p2p_export(amaru_model *m, void *out128, char *msg, int msglen) {
     try {
         if (msg && msglen > 0) msg[0] = 0;
@@ -299,10 +434,7 @@ extern "C" int amaru_p2p_export(amaru_model *m, void *out128, char *msg, int msg
         HaloComm *hc = static_cast<HaloComm *>(m->comm);
         AMARU_REQUIRE(hc && m->nranks > 1 && m->nranks <= P2P_MAXR, AMARU_ERR_ARG, "amaru_p2p_export: needs a partitioned handle of at most 16 ranks");
         CUDA_CHECK(cudaSetDevice(m->device));
-        if (!hc->d_win) {
-            CUDA_CHECK(cudaMalloc(&hc->d_win, sizeof(P2PWin)));
-            CUDA_CHECK(cudaMemset(hc->d_win, 0, sizeof(P2PWin)));
-        }
+        ensure_window(m, hc);
         cudaIpcMemHandle_t h[2];
         CUDA_CHECK(cudaIpcGetMemHandle(&h[0], hc->d_win));
         CUDA_CHECK(cudaIpcGetMemHandle(&h[1], m->d_p));
@@ -344,19 +476,7 @@ extern "C" int amaru_p2p_connect(amaru_model *m, const void *all_handles, const 
             hc->opened.push_back(pp);
             peer_p[(size_t)q] = static_cast<double *>(pp);
         }
-        const size_t nn = (size_t)std::max(hc->nneigh, 1);
-        CUDA_CHECK(cudaMalloc(&hc->d_peer_p, nn * sizeof(double *)));
-        CUDA_CHECK(cudaMalloc(&hc->d_peer_start, nn * sizeof(int64_t)));
-        CUDA_CHECK(cudaMalloc(&hc->d_send_ptr, (nn + 1) * sizeof(int64_t)));
-        CUDA_CHECK(cudaMalloc(&hc->d_neigh, nn * sizeof(int)));
-        CUDA_CHECK(cudaMalloc(&hc->d_counter, sizeof(unsigned int)));
-        CUDA_CHECK(cudaMemset(hc->d_counter, 0, sizeof(unsigned int)));
-        CUDA_CHECK(cudaMemcpy(hc->d_peer_p, peer_p.data(), hc->nneigh * sizeof(double *), cudaMemcpyHostToDevice));
-        if (hc->nneigh) CUDA_CHECK(cudaMemcpy(hc->d_peer_start, peer_recv_start, hc->nneigh * sizeof(int64_t), cudaMemcpyHostToDevice));
-        CUDA_CHECK(cudaMemcpy(hc->d_send_ptr, hc->send_ptr.data(), (hc->nneigh + 1) * sizeof(int64_t), cudaMemcpyHostToDevice));
-        if (hc->nneigh) CUDA_CHECK(cudaMemcpy(hc->d_neigh, hc->neigh.data(), hc->nneigh * sizeof(int), cudaMemcpyHostToDevice));
-        CUDA_CHECK(cudaDeviceSynchronize());
-        hc->p2p_ready = true;
+        upload_peer_tables(m, hc, peer_p, {}, peer_recv_start);   // x keeps the NCCL exchange between processes
         return AMARU_OK;
     } catch (const AmaruError &e) {
         if (msg && msglen > 0) snprintf(msg, (size_t)msglen, "%s", e.msg.c_str());

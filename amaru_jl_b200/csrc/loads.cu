@@ -242,8 +242,9 @@ int amaru_loadset_create(amaru_model *m, int shape, int64_t nents, const int32_t
         AMARU_REQUIRE(m && out, AMARU_ERR_ARG, "amaru_loadset_create: null argument");
         *out = nullptr;
         AMARU_REQUIRE(nents >= 0 && (nents == 0 || nodes), AMARU_ERR_ARG, "amaru_loadset_create: null node list");
-        AMARU_REQUIRE(m->nranks == 1, AMARU_ERR_UNSUPPORTED,
-                      "amaru_loadset_create: single-GPU handles only (partitioned runs integrate loads per rank on the host)");
+        // a multi-GPU handle of one process integrates on its first GPU with the global arrays its wrapper keeps (group.cu)
+        AMARU_REQUIRE(m->nranks == 1 || m->grp, AMARU_ERR_UNSUPPORTED,
+                      "amaru_loadset_create: rank-level partitioned handles integrate loads per rank on the host");
         ShapeInfo si;
         AMARU_REQUIRE(amaru_shape_info(shape, si), AMARU_ERR_UNSUPPORTED, "amaru_loadset_create: unknown shape");
         // facets: shape dimension ndim-1 (distributed.jl:92-93 rejects surfaces loads on 3D edges); cells: dimension ndim

@@ -291,25 +291,23 @@ void amaru_spmv(amaru_model *m, const double *A, const double *x, double *y, int
 
 // y = A x with the system matrix of the solve (unmasked, no dot): matrix-free or from the assembled block-CSR values
 static void amaru_system_product(amaru_model *m, const double *x, double *y) {
-    if (m->op_ebe) amaru_ebe_apply(m, x, y, 0, 0, 0, 0);
+    if (m->op_ebe && !m->blended) amaru_ebe_apply(m, x, y, 0, 0, 0, 0);
     else amaru_spmv(m, m->d_A, x, y, 0);
 }
 
 static void spmv_dot(amaru_model *m, const double *A, const double *x, double *y, int finalize) {
     cudaEvent_t e0 = nullptr, e1 = nullptr;
-    if (m->profiling) {
+    if (m->profiling) {   // the pool owns the events from the moment they exist (released with the profile / the handle)
         CUDA_CHECK(cudaEventCreate(&e0));
+        m->ev_pool.push_back(e0);
         CUDA_CHECK(cudaEventCreate(&e1));
+        m->ev_pool.push_back(e1);
         CUDA_CHECK(cudaEventRecord(e0, m->stream));
     }
-    if (m->op_ebe && A == m->d_A) amaru_ebe_apply(m, x, y, 1, 1, 1, finalize);               // matrix-free (ebe.cu)
+    if (m->op_ebe && !m->blended && A == m->d_A) amaru_ebe_apply(m, x, y, 1, 1, 1, finalize);               // matrix-free (ebe.cu)
     else if (m->use_sym && A == m->d_A) amaru_spmv_sym_launch(m, x, y, 1, 1, 1, finalize);   // half the bytes (spmv.cu)
     else amaru_spmv_launch(m, A, x, y, 1, 1, 1, finalize);
-    if (m->profiling) {
-        CUDA_CHECK(cudaEventRecord(e1, m->stream));
-        m->ev_pool.push_back(e0);
-        m->ev_pool.push_back(e1);
-    }
+    if (m->profiling) CUDA_CHECK(cudaEventRecord(e1, m->stream));
 }
 
 // test / measurement hook: q = A p with the handle's CG operator; masked != 0 also runs the fused p.Ap (returned)
@@ -371,20 +369,17 @@ static void cg_loop(amaru_model *m, double rtol, int maxit, SolveInfo &info) {
     // 3 launches of a few microseconds per iteration) are launch-bound otherwise.  Not used while the SpMV is being timed
     // with events, nor on partitioned handles (NCCL calls sit between the kernels).
     cudaGraphExec_t gexec = nullptr;
-    const bool use_graph = !multi && !m->profiling && m->cg_graph;
+    // peer-memory exchanges are plain kernels with device-resident epochs, so partitioned handles replay graphs too; with
+    // NCCL calls between the kernels (the default between processes until amaru_p2p_enable) the batch is launched directly
+    const bool p2p = multi && amaru_comm_is_p2p(m);
+    const bool use_graph = !m->profiling && m->cg_graph && (!multi || p2p);
     bool finished = false;
     int64_t batch_launches = 0;
-    while (!finished) {
-        if (use_graph && gexec) {
-            CUDA_CHECK(cudaGraphLaunch(gexec, m->stream));
-            m->launches += batch_launches;
-        } else {
-        const int64_t l0 = m->launches;
-        if (use_graph) CUDA_CHECK(cudaStreamBeginCapture(m->stream, cudaStreamCaptureModeThreadLocal));
+    auto one_batch = [&]() {
         for (int it = 0; it < CG_BATCH; it++) {
             if (multi) amaru_halo_exchange(m, m->d_p);
             spmv_dot(m, m->d_A, m->d_p, m->d_q, fin);
-            // multi-GPU: per iteration = halo exchange, SpMV, all-reduce(p.Ap), update, all-reduce(r.z, r.r), one scalar
+            // multi-GPU: per iteration = halo exchange, operator, all-reduce(p.Ap), update, all-reduce(r.z, r.r), one scalar
             // kernel, p-update; the partial dots are staged by the producing kernels' last blocks and alpha is formed by
             // the consumer (k_cg_update) from the all-reduced value
             if (multi) amaru_allreduce_sum(m, m->d_scal->acc, 1);
@@ -398,19 +393,41 @@ static void cg_loop(amaru_model *m, double rtol, int maxit, SolveInfo &info) {
             k_cg_pupdate<<<node_grid(m, nloc), ROW_THREADS, 0, m->stream>>>(nloc, m->d_z, m->d_p, m->d_scal);
             m->launches += 2;
         }
-        if (use_graph) {
-            cudaGraph_t graph = nullptr;
-            CUDA_CHECK(cudaStreamEndCapture(m->stream, &graph));
-            CUDA_CHECK(cudaGraphInstantiate(&gexec, graph, 0));
-            CUDA_CHECK(cudaGraphDestroy(graph));
-            CUDA_CHECK(cudaGraphLaunch(gexec, m->stream));
-            batch_launches = m->launches - l0;
+    };
+    try {
+        while (!finished) {
+            if (use_graph && gexec) {
+                CUDA_CHECK(cudaGraphLaunch(gexec, m->stream));
+                m->launches += batch_launches;
+            } else if (use_graph) {
+                const int64_t l0 = m->launches;
+                CUDA_CHECK(cudaStreamBeginCapture(m->stream, cudaStreamCaptureModeThreadLocal));
+                cudaGraph_t graph = nullptr;
+                try {
+                    one_batch();
+                } catch (...) {   // leave capture mode before unwinding, else the stream stays unusable
+                    cudaStreamEndCapture(m->stream, &graph);
+                    if (graph) cudaGraphDestroy(graph);
+                    throw;
+                }
+                CUDA_CHECK(cudaStreamEndCapture(m->stream, &graph));
+                const cudaError_t ie = cudaGraphInstantiate(&gexec, graph, 0);
+                cudaGraphDestroy(graph);
+                CUDA_CHECK(ie);
+                CUDA_CHECK(cudaGraphLaunch(gexec, m->stream));
+                batch_launches = m->launches - l0;
+            } else {
+                one_batch();
+            }
+            CUDA_CHECK(cudaGetLastError());
+            CUDA_CHECK(cudaMemcpyAsync(h, m->d_scal, sizeof(CgScalars), cudaMemcpyDeviceToHost, m->stream));
+            CUDA_CHECK(cudaStreamSynchronize(m->stream));
+            if (p2p) amaru_comm_check(m);
+            finished = h->done != 0;
         }
-        }
-        CUDA_CHECK(cudaGetLastError());
-        CUDA_CHECK(cudaMemcpyAsync(h, m->d_scal, sizeof(CgScalars), cudaMemcpyDeviceToHost, m->stream));
-        CUDA_CHECK(cudaStreamSynchronize(m->stream));
-        finished = h->done != 0;
+    } catch (...) {
+        if (gexec) cudaGraphExecDestroy(gexec);
+        throw;
     }
     if (gexec) cudaGraphExecDestroy(gexec);
     info.iters = h->iters;

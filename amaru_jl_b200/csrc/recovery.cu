@@ -353,7 +353,7 @@ extern "C" {
 int amaru_recovery_create(amaru_model *m, const uint8_t *at_bound, char *msg, int msglen) {
     return guarded(msg, msglen, [&]() {
         AMARU_REQUIRE(m && at_bound, AMARU_ERR_ARG, "amaru_recovery_create: null argument");
-        AMARU_REQUIRE(m->nranks == 1, AMARU_ERR_UNSUPPORTED, "amaru_recovery_create: single-GPU handles only");
+        AMARU_REQUIRE(m->nranks == 1 || m->grp, AMARU_ERR_UNSUPPORTED, "amaru_recovery_create: not for rank-level partitioned handles");
         CUDA_CHECK(cudaSetDevice(m->device));
         CUDA_CHECK(cudaStreamSynchronize(m->stream));
         amaru_recovery_destroy(m);
@@ -610,6 +610,7 @@ int amaru_recover_nodal(amaru_model *m, double *V, char *msg, int msglen) {
         CUDA_CHECK(cudaSetDevice(m->device));
         const int nf = r->nfields;
         if (nf == 0) return AMARU_OK;
+        if (m->grp) amaru_group_refresh_output_state(m);   // multi-GPU handle: gather the owners' IP state first
         if (r->npatch > 0) {
             const int gfit = (int)std::max<int64_t>(1, std::min<int64_t>((r->npatch + 3) / 4, (int64_t)m->nsm * 16));
             for (int g = 0; g < NGROUPS; g++) {

@@ -65,6 +65,8 @@ __global__ void __launch_bounds__(NT) k_update(UpdArgs p) {
     if (active) {
         const double *X = sX + e * NN * ND, *dN = sdN + q * NN * ND, *U = sU + e * NN * ND;
         const double det = am_jacobian<NN, ND>(X, dN, Ji);
+        // no detJ > 0 test here: the reference's update_elem! has none (mech-solid.jl:243-279; only elem_stiffness :150 and
+        // elem_mass :194 raise), and with fixed coordinates the assembly that precedes every update has already tested it
         coef = det * sw[q] * p.th;
         const int64_t ip = p.ip_off + (e0 + e) * NIP + q;
         if (p.mode == 0) {

@@ -31,7 +31,8 @@ def _round_sig(x, sig):
 
 
 def solve_dynamic(ana: DynamicAnalysis, tol=0.01, dTmin=1e-7, dTmax=0.1, rspan=0.01, scheme="FE", maxits=5, autoinc=False,
-                  quiet=True, alpha=0.0, beta=0.0, cg_rtol=1e-10, cg_maxit=200000, precond="block-jacobi", device=0) -> ReturnStatus:
+                  quiet=True, alpha=0.0, beta=0.0, cg_rtol=1e-10, cg_maxit=200000, precond="block-jacobi", device=0, ngpus=1,
+                  partitioner="rcb", keep_fields=False) -> ReturnStatus:
     if str(scheme).lstrip(":") != "FE":
         raise AmaruError("solve!: only scheme=:FE is available on the B200 path")
     pc = L.PRECOND[precond] if isinstance(precond, str) else int(precond)
@@ -39,7 +40,8 @@ def solve_dynamic(ana: DynamicAnalysis, tol=0.01, dTmin=1e-7, dTmax=0.1, rspan=0
         raise AmaruError("stage_iterator!: No stages have been set")
     status = success()
     for stage in [s for s in ana.stages if s.status != "done"]:
-        status = _dyn_stage_solver(ana, stage, tol, dTmin, dTmax, maxits, autoinc, alpha, beta, cg_rtol, cg_maxit, pc, device)
+        status = _dyn_stage_solver(ana, stage, tol, dTmin, dTmax, maxits, autoinc, alpha, beta, cg_rtol, cg_maxit, pc, device,
+                                   ngpus, partitioner, keep_fields)
         if not status.success:
             stage.status = "failed"
             break
@@ -47,7 +49,8 @@ def solve_dynamic(ana: DynamicAnalysis, tol=0.01, dTmin=1e-7, dTmax=0.1, rspan=0
     return status
 
 
-def _dyn_stage_solver(ana, stage, tol, dTmin, dTmax, maxits, autoinc, alpha, beta, cg_rtol, cg_maxit, pc, device):
+def _dyn_stage_solver(ana, stage, tol, dTmin, dTmax, maxits, autoinc, alpha, beta, cg_rtol, cg_maxit, pc, device,
+                      ngpus=1, partitioner="rcb", keep_fields=False):
     model = ana.model
     log = ana.log
     log.append(f"Dynamic FE analysis: Stage {stage.id}")
@@ -56,7 +59,7 @@ def _dyn_stage_solver(ana, stage, tol, dTmin, dTmax, maxits, autoinc, alpha, bet
     eqid, nu, setup = model.configure_dofs(stage.bcs)
     ndofs = eqid.size
     eqflat = eqid.reshape(-1)
-    dm = L.DeviceModel(model.flatten(), eqid, ndofs, nu, device=device)
+    dm = L.DeviceModel(model.flatten(), eqid, ndofs, nu, device=device, ngpus=ngpus, partitioner=partitioner)
     try:
         st = model.state
         dm.set_state(st["sigma"], st["eps"], st["epa"], st["dlam"])
@@ -178,7 +181,10 @@ def _dyn_stage_solver(ana, stage, tol, dTmin, dTmax, maxits, autoinc, alpha, bet
                         os.makedirs(ana.outdir, exist_ok=True)
                         update_output_data(model, dm)                 # nodal recovery on the device
                         save(model, os.path.join(ana.outdir, f"{ana.outkey}-{ana.out}.vtu"))
-                ana.records.append(dict(stage=stage.id, inc=inc, T=T, t=t, U=model.U.copy(), V=model.V.copy(), A=model.A.copy()))
+                rec = dict(stage=stage.id, inc=inc, T=T, t=t)             # scalars only; full fields are opt-in
+                if keep_fields:
+                    rec.update(U=model.U.copy(), V=model.V.copy(), A=model.A.copy())
+                ana.records.append(rec)
                 if autoinc:
                     if dTbk > 0.0:
                         dT = min(dTbk, Tcheck - T)

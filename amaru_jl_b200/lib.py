@@ -19,6 +19,8 @@ OK = 0
 FAIL_MATERIAL, FAIL_NAN, FAIL_SINGULAR, FAIL_NEG_JACOBIAN, FAIL_CG_NOCONV, FAIL_TANGENT = 1, 2, 3, 4, 5, 6
 ERR_ARG, ERR_CUDA, ERR_NO_DEVICE, ERR_UNSUPPORTED, ERR_COMM = -1, -2, -3, -4, -5
 PRECOND_JACOBI, PRECOND_BLOCK_JACOBI = 0, 1
+PARTITION_RCB, PARTITION_METIS = 0, 1
+PARTITIONER = {"rcb": PARTITION_RCB, "metis": PARTITION_METIS}
 PRECOND = {"jacobi": PRECOND_JACOBI, "block-jacobi": PRECOND_BLOCK_JACOBI, "block_jacobi": PRECOND_BLOCK_JACOBI,
            "bjacobi": PRECOND_BLOCK_JACOBI}
 
@@ -33,8 +35,12 @@ SYMBOLS = {
     "amaru_device_count": (C.c_int, []),
     "amaru_version": (C.c_char_p, []),
     "amaru_create": (C.c_int, [C.c_int, C.c_int, C.c_double, C.c_int64, _dp, C.c_int, _i32p, _i64p, _i32p, _i32p,
-                               C.c_int, _i32p, _dp, _i32p, C.c_int64, C.c_int64, C.c_int, C.POINTER(_vp), C.c_char_p,
-                               C.c_int]),
+                               C.c_int, _i32p, _dp, _i32p, C.c_int64, C.c_int64, C.c_int, _i32p, C.c_int,
+                               C.POINTER(_vp), C.c_char_p, C.c_int]),
+    "amaru_ngpus": (C.c_int, [_vp]),
+    "amaru_partition_elements_abi": (C.c_int, [C.c_int, C.c_int, C.c_int64, _dp, C.c_int, _i32p, _i64p, _i32p, _i32p,
+                                               C.c_char_p, C.c_int]),
+    "amaru_comm_selftest": (C.c_int, [_vp, C.c_int, C.c_char_p, C.c_int]),
     "amaru_create_partitioned": (C.c_int, [C.c_int, C.c_int, C.c_double, C.c_int64, C.c_int64, _dp,
                                            C.c_int, _i32p, _i64p, _i32p, _i32p, C.c_int, _i32p, _dp, _i32p,
                                            C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, _i32p, _i64p, _i32p, _i64p,
@@ -53,6 +59,8 @@ SYMBOLS = {
     "amaru_state_backup": (C.c_int, [_vp]),
     "amaru_state_restore": (C.c_int, [_vp]),
     "amaru_assemble_K": (C.c_int, [_vp, C.c_char_p, C.c_int]),
+    "amaru_tangent_save": (C.c_int, [_vp, C.c_char_p, C.c_int]),
+    "amaru_tangent_blend": (C.c_int, [_vp, C.c_double, C.c_double, C.c_char_p, C.c_int]),
     "amaru_get_csr": (C.c_int, [_vp, _i64p, _i32p, _dp, C.c_char_p, C.c_int]),
     "amaru_solve": (C.c_int, [_vp, _dp, _dp, C.c_double, C.c_int, C.c_int, C.POINTER(C.c_int), _dp, C.c_char_p,
                               C.c_int]),
@@ -137,10 +145,13 @@ class AmaruStatus(AmaruError):
 class DeviceModel:
     """One stage's device handle (``amaru_create`` ... ``amaru_destroy``)."""
 
-    def __init__(self, flat: dict, eqid: np.ndarray, ndofs: int, nu: int, device: int = 0, view=None, nccl_uid=None):
-        """Single-GPU handle (``amaru_create``), or — with ``view`` (partition.LocalView) and the 128-byte ``nccl_uid`` —
-        this rank's handle of a partitioned model (``amaru_create_partitioned``); ``flat``/``eqid`` are then the LOCAL
-        arrays from ``partition.local_flat`` while ``ndofs``/``nu`` stay global."""
+    def __init__(self, flat: dict, eqid: np.ndarray, ndofs: int, nu: int, device: int = 0, view=None, nccl_uid=None,
+                 ngpus: int = 1, devices=None, partitioner="rcb"):
+        """``amaru_create``: one handle over ``ngpus`` B200s of this box (``devices`` = their ordinals, default
+        ``device, device+1, ...``; the library partitions the mesh itself), or — with ``view`` (partition.LocalView) and the
+        128-byte ``nccl_uid`` — this rank's handle of a model partitioned by the caller, one process per GPU
+        (``amaru_create_partitioned``); ``flat``/``eqid`` are then the LOCAL arrays from ``partition.local_flat`` while
+        ``ndofs``/``nu`` stay global."""
         self.lib = load()
         self._msg = C.create_string_buffer(512)
         self.ndofs, self.nu = int(ndofs), int(nu)
@@ -155,12 +166,16 @@ class DeviceModel:
         h = _vp()
         self.view = view
         if view is None:
+            devs = np.ascontiguousarray(devices if devices is not None else np.arange(int(ngpus)) + int(device), dtype=np.int32)
+            if devs.size != int(ngpus):
+                raise AmaruError("DeviceModel: len(devices) must equal ngpus")
+            part = PARTITIONER[partitioner] if isinstance(partitioner, str) else int(partitioner)
             st = self.lib.amaru_create(int(flat["ndim"]), int(flat["stressmodel"]), float(flat["thickness"]),
                                        coords.shape[0], _d(coords), len(bshape), bshape.ctypes.data_as(_i32p),
                                        bnelem.ctypes.data_as(_i64p), conn.ctypes.data_as(_i32p),
                                        emat.ctypes.data_as(_i32p), len(mkind), mkind.ctypes.data_as(_i32p), _d(mpar),
-                                       eq.ctypes.data_as(_i32p), self.ndofs, self.nu, int(device), C.byref(h), self._msg,
-                                       len(self._msg))
+                                       eq.ctypes.data_as(_i32p), self.ndofs, self.nu, int(ngpus),
+                                       devs.ctypes.data_as(_i32p), part, C.byref(h), self._msg, len(self._msg))
         else:
             neigh = np.ascontiguousarray(view.neigh, dtype=np.int32)
             sptr = np.ascontiguousarray(view.send_ptr, dtype=np.int64)
@@ -199,6 +214,14 @@ class DeviceModel:
             self.close()
         except Exception:
             pass
+
+    @property
+    def ngpus(self):
+        return self.lib.amaru_ngpus(self.h)
+
+    def comm_selftest(self, skip_rank=-1):
+        """Failure injection for the bounded peer-memory waits (multi-GPU handles); raises AmaruStatus(ERR_COMM) on timeout."""
+        self._check(self.lib.amaru_comm_selftest(self.h, int(skip_rank), self._msg, len(self._msg)))
 
     @property
     def nnz(self):
@@ -244,6 +267,12 @@ class DeviceModel:
     # -- the three hot calls
     def assemble_K(self):
         self._check(self.lib.amaru_assemble_K(self.h, self._msg, len(self._msg)))
+
+    def tangent_save(self):
+        self._check(self.lib.amaru_tangent_save(self.h, self._msg, len(self._msg)))
+
+    def tangent_blend(self, a1, a2):
+        self._check(self.lib.amaru_tangent_blend(self.h, float(a1), float(a2), self._msg, len(self._msg)))
 
     def solve(self, U, F, cg_rtol=1e-10, cg_maxit=100000, precond=PRECOND_BLOCK_JACOBI):
         """In place on U[:nu] and F[nu:] like solve_system!; returns (iters, relres)."""
@@ -491,6 +520,24 @@ def mesh_block(shape_id, c0, c1, nx, ny, nz):
     if st != OK:
         raise AmaruStatus(st, msg.value.decode(errors="replace"))
     return coords, conn
+
+
+def partition_elements(flat: dict, nparts: int, partitioner="rcb"):
+    """The element partition ``amaru_create(ngpus=nparts)`` uses (host only): part index per element, ABI element order."""
+    lib = load()
+    coords = np.ascontiguousarray(flat["coords"], dtype=np.float64)
+    bshape = np.ascontiguousarray(flat["batch_shape"], dtype=np.int32)
+    bnelem = np.ascontiguousarray(flat["batch_nelem"], dtype=np.int64)
+    conn = np.ascontiguousarray(flat["conn"], dtype=np.int32).reshape(-1)
+    out = np.zeros(int(bnelem.sum()), dtype=np.int32)
+    msg = C.create_string_buffer(256)
+    part = PARTITIONER[partitioner] if isinstance(partitioner, str) else int(partitioner)
+    st = lib.amaru_partition_elements_abi(part, int(nparts), coords.shape[0], _d(coords), len(bshape),
+                                          bshape.ctypes.data_as(_i32p), bnelem.ctypes.data_as(_i64p),
+                                          conn.ctypes.data_as(_i32p), out.ctypes.data_as(_i32p), msg, 256)
+    if st != OK:
+        raise AmaruStatus(st, msg.value.decode(errors="replace"))
+    return out
 
 
 def configure_dofs(prescribed):

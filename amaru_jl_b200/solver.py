@@ -11,7 +11,10 @@ of every iteration go through the C ABI:
     copyto!.(StateBk, State)                -> amaru_state_backup        (:391)
 
 Solver keyword arguments are ``mech_solver_params`` (mech-solver.jl:155-168) plus the GPU knobs ``cg_rtol``,
-``cg_maxit``, ``precond`` and ``device``.  Only scheme=:FE is wired (the reference default); there is no CPU fallback.
+``cg_maxit``, ``precond``, ``device`` and ``ngpus`` / ``partitioner`` (one handle over N B200s of the box; the driver
+below does not change).  The schemes :FE (default), :ME, :BE and :Ralston are wired (mech-solver.jl:279-288,341-350); there
+is no CPU fallback.  ``ana.records`` gets one line of scalars per converged increment; ``keep_fields=True`` additionally
+keeps copies of U and F per increment (hundreds of MB each at the benchmark size, so off by default).
 """
 from __future__ import annotations
 
@@ -27,6 +30,11 @@ from .model import AmaruError, MechAnalysis, ReturnStatus, failure, success
 _EPS = float(np.finfo(np.float64).eps)
 
 
+# scheme -> (p1, q11, a1, a2)   (mech-solver.jl:279-288)
+_SCHEMES = {"FE": (1.0, 1.0, None, None), "ME": (1.0, 1.0, 0.5, 0.5), "BE": (1.0, 1.0, 0.0, 1.0),
+            "Ralston": (2 / 3, 2 / 3, 1 / 4, 3 / 4)}
+
+
 def _round_sig(x, sig):
     if x == 0:
         return 0.0
@@ -34,13 +42,15 @@ def _round_sig(x, sig):
 
 
 def solve(ana: MechAnalysis, tol=0.01, rspan=0.01, rtol=0.01, dT0=0.01, dTmin=1e-7, dTmax=0.1, scheme="FE", maxits=5,
-          autoinc=False, quiet=True, cg_rtol=1e-10, cg_maxit=200000, precond="block-jacobi", device=0) -> ReturnStatus:
+          autoinc=False, quiet=True, cg_rtol=1e-10, cg_maxit=200000, precond="block-jacobi", device=0, ngpus=1,
+          partitioner="rcb", keep_fields=False) -> ReturnStatus:
     if not tol > 0 or not rtol > 0 or not 0 < rspan < 1 or not 0 < dT0 <= 1 or not 0 < dTmin < 1 or not 0 < dTmax < 1:
         raise AmaruError("solve!: invalid solver parameters")
     if not 1 <= maxits <= 10:
         raise AmaruError("solve!: 1<=maxits<=10 required")
-    if str(scheme).lstrip(":") != "FE":
-        raise AmaruError("solve!: only scheme=:FE is available on the B200 path")
+    scheme = str(scheme).lstrip(":")
+    if scheme not in _SCHEMES:
+        raise AmaruError("solve!: scheme must be one of :FE, :ME, :BE, :Ralston")
     pc = L.PRECOND[precond] if isinstance(precond, str) else int(precond)
     stages = [s for s in ana.stages if s.status != "done"]           # solver.jl:88 (resume at first stage not done)
     if not ana.stages:
@@ -48,7 +58,7 @@ def solve(ana: MechAnalysis, tol=0.01, rspan=0.01, rtol=0.01, dT0=0.01, dTmin=1e
     status = success()
     for stage in stages:
         status = _mech_stage_solver(ana, stage, tol, rtol, dT0, dTmin, dTmax, rspan, maxits, autoinc, quiet, cg_rtol,
-                                    cg_maxit, pc, device)
+                                    cg_maxit, pc, device, scheme, ngpus, partitioner, keep_fields)
         if not status.success:
             stage.status = "failed"
             break
@@ -57,7 +67,7 @@ def solve(ana: MechAnalysis, tol=0.01, rspan=0.01, rtol=0.01, dT0=0.01, dTmin=1e
 
 
 def _mech_stage_solver(ana, stage, tol, rtol, dT0, dTmin, dTmax, rspan, maxits, autoinc, quiet, cg_rtol, cg_maxit, pc,
-                       device):
+                       device, scheme="FE", ngpus=1, partitioner="rcb", keep_fields=False):
     model = ana.model
     log = ana.log
     log.append(f"Mechanical FE analysis: Stage {stage.id}")
@@ -72,7 +82,8 @@ def _mech_stage_solver(ana, stage, tol, rtol, dT0, dTmin, dTmax, rspan, maxits, 
         model.U[...] = 0.0
         model.F[...] = 0.0
 
-    dm = L.DeviceModel(model.flatten(), eqid, ndofs, nu, device=device)
+    p1, q11, a1, a2 = _SCHEMES[scheme]
+    dm = L.DeviceModel(model.flatten(), eqid, ndofs, nu, device=device, ngpus=ngpus, partitioner=partitioner)
     try:
         st = model.state                                              # IP state persists across stages (:245)
         dm.set_state(st["sigma"], st["eps"], st["epa"], st["dlam"])
@@ -118,18 +129,30 @@ def _mech_stage_solver(ana, stage, tol, rtol, dT0, dTmin, dTmax, rspan, maxits, 
                 t0 = time.perf_counter()
                 try:
                     dm.assemble_K()                                   # K = mount_K(...)
-                    dUitr = np.ascontiguousarray(1.0 * dUi)
-                    Rtr = np.ascontiguousarray(1.0 * R)
+                    dUitr = np.ascontiguousarray(p1 * dUi)
+                    Rtr = np.ascontiguousarray(q11 * R)
                     cg_it, cg_rr = dm.solve(dUitr, Rtr, cg_rtol, cg_maxit, pc)   # solve_system!
                     dm.state_restore()                                # copyto!.(State, StateBk)
                     dUt = dUa + dUitr
                     dm.update_state(dUt, dFin)                        # ΔFin, status = update_state!
+                    if scheme == "FE":
+                        dUi = dUitr
+                    else:                                             # corrector step (:341-350)
+                        dm.tangent_save()
+                        dm.assemble_K()                               # K2 = mount_K(...) on the predictor's state
+                        dm.tangent_blend(a1, a2)                      # K = a1*K + a2*K2
+                        dUi = np.ascontiguousarray(dUi)
+                        Rc2 = np.ascontiguousarray(1.0 * R)           # solve_system! overwrites R[nu+1:end] with reactions
+                        it2, cg_rr = dm.solve(dUi, Rc2, cg_rtol, cg_maxit, pc)
+                        cg_it += it2
+                        dm.state_restore()
+                        dUt = dUa + dUi
+                        dm.update_state(dUt, dFin)
                 except L.AmaruStatus as e:
                     if e.code < 0:
                         raise
                     syserror, sysmsg = True, e.message
                     break
-                dUi = dUitr
                 dUa += dUi
                 R[:] = dFex - dFin
                 R[nu:] = 0.0
@@ -172,7 +195,10 @@ def _mech_stage_solver(ana, stage, tol, rtol, dT0, dTmin, dTmax, rspan, maxits, 
                         os.makedirs(ana.outdir, exist_ok=True)
                         update_output_data(model, dm)                 # nodal recovery on the device
                         save(model, os.path.join(ana.outdir, f"{ana.outkey}-{ana.out}.vtu"))
-                ana.records.append(dict(stage=stage.id, inc=inc, T=T, U=model.U.copy(), F=model.F.copy()))
+                rec = dict(stage=stage.id, inc=inc, T=T, residue=res, nits=nits)   # scalars only
+                if keep_fields:
+                    rec.update(U=model.U.copy(), F=model.F.copy())
+                ana.records.append(rec)
                 if autoinc:                                           # :426-455
                     if dTbk > 0.0:
                         dT = min(dTbk, Tcheck - T)

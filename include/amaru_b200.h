@@ -94,17 +94,38 @@ const char *amaru_version(void);
  *   elem_mat      [nelem_total] index into the material table
  *   mat_kind      [nmats] AMARU_MAT_*;  mat_params [nmats*8]
  *   eqid          [nnodes*ndim] eq_id of (node, ux|uy|uz); unknown dofs are 0..nu-1
- *   device        CUDA device ordinal
+ *   ngpus         number of B200s of this box the handle spreads over.  1: everything on devices[0]
+ *                 (device 0 when devices is NULL).  N > 1: the mesh is partitioned inside the library (element partition,
+ *                 node ownership, duplicated halo elements), every GPU assembles the CSR rows of its own nodes and one
+ *                 host thread per GPU drives it; the CG loop exchanges halo entries and scalars through NVLink peer
+ *                 memory (cudaDeviceEnablePeerAccess), no NCCL, no extra processes.  Every other entry point below
+ *                 takes the same handle and the same global-length host vectors, so `solve!(ana)` stays ONE process
+ *                 (reference src/mech/mech-solver.jl:172-181).
+ *   devices       [ngpus] CUDA device ordinals, or NULL for 0..ngpus-1
+ *   partitioner   AMARU_PARTITION_RCB | AMARU_PARTITION_METIS (ignored for ngpus == 1)
  * Builds on the device: the element colouring, the symbolic block-CSR pattern, the scatter map.
  * IP state starts at zero (the IpState constructors, e.g. von-mises.jl:35-42).
  */
+#define AMARU_PARTITION_RCB 0   /* recursive coordinate bisection of the element centroids (deterministic, compact boxes)   */
+#define AMARU_PARTITION_METIS 1 /* METIS k-way on the element dual graph (facet adjacency); falls back to RCB on tiny meshes */
 int amaru_create(int ndim, int stressmodel, double thickness,
                  int64_t nnodes, const double *coords,
                  int nbatches, const int32_t *batch_shape, const int64_t *batch_nelem,
                  const int32_t *conn, const int32_t *elem_mat,
                  int nmats, const int32_t *mat_kind, const double *mat_params,
                  const int32_t *eqid, int64_t ndofs, int64_t nu,
-                 int device, amaru_model **out, char *msg, int msglen);
+                 int ngpus, const int32_t *devices, int partitioner,
+                 amaru_model **out, char *msg, int msglen);
+/* number of GPUs behind the handle */
+int amaru_ngpus(const amaru_model *m);
+/* The element partition amaru_create(ngpus = nparts) would use: elem_part[nelem_total] in ABI element order.  Host only. */
+int amaru_partition_elements_abi(int partitioner, int nparts, int64_t nnodes, const double *coords, int nbatches,
+                                 const int32_t *batch_shape, const int64_t *batch_nelem, const int32_t *conn,
+                                 int32_t *elem_part, char *msg, int msglen);
+/* Failure injection for the bounded peer-memory waits of multi-GPU handles: every GPU but `skip_rank` enters one scalar
+ * all-reduce; returns AMARU_ERR_COMM after the timeout (AMARU_P2P_TIMEOUT_MS, default 10 s) instead of hanging, and the
+ * handle must be destroyed afterwards.  skip_rank < 0: nobody is skipped, returns AMARU_OK. */
+int amaru_comm_selftest(amaru_model *m, int skip_rank, char *msg, int msglen);
 
 /* Multi-GPU variant (one process per GPU; the reference has no distributed path).  This rank passes its
  * LOCAL view of the partitioned mesh: `nnodes` local nodes of which the first `nowned` are owned (the rest are ghosts,
@@ -157,6 +178,14 @@ int amaru_state_restore(amaru_model *m);
 /* mount_K (src/mech/mech-solver.jl:78-110) with elem_stiffness (src/mech/elem/mech-solid.jl:124-166) and
  * calcD of the three materials; K stays on the device. */
 int amaru_assemble_K(amaru_model *m, char *msg, int msglen);
+
+/* Predictor-corrector schemes :ME / :BE / :Ralston (src/mech/mech-solver.jl:279-288,341-350): after the predictor's
+ * mount_K -> amaru_tangent_save keeps that K; after the corrector's `K2 = mount_K(...)` (amaru_assemble_K on the updated
+ * state) amaru_tangent_blend forms `K = a1*K + a2*K2` in place, which the next amaru_solve uses.  A genuine blend (a1 != 0)
+ * is no longer described by the per-IP tangent data of the matrix-free operator, so that solve runs the block-CSR SpMV;
+ * the next amaru_assemble_K restores the default. */
+int amaru_tangent_save(amaru_model *m, char *msg, int msglen);
+int amaru_tangent_blend(amaru_model *m, double a1, double a2, char *msg, int msglen);
 
 /* Symbolic CSR pattern in eq_id numbering (== the CSC of the reference's symbolic K, which is structurally
  * symmetric) and the assembled values.  rowptr [ndofs+1], colind/val [nnz], columns ascending per row.

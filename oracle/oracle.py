@@ -280,12 +280,15 @@ def _round_sig(x, sig):
 
 
 def mech_stage_solver(om: OracleModel, Uex, Fex, nincs=1, tol=0.01, rtol=0.01, rspan=0.01, dT0=0.01,
-                      dTmin=1e-7, dTmax=0.1, maxits=5, autoinc=False, nouts=0, solver=None, log=None):
-    """mech_stage_solver! (mech-solver.jl:186-492), scheme :FE.  Vectors are in eq_id order.
+                      dTmin=1e-7, dTmax=0.1, maxits=5, autoinc=False, nouts=0, solver=None, log=None, scheme="FE"):
+    """mech_stage_solver! (mech-solver.jl:186-492), schemes :FE / :ME / :BE / :Ralston (:279-288, predictor-corrector
+    :341-350).  Vectors are in eq_id order.
 
     -> dict(success, message, U, F, incs, its, history=[(T, U, F)])
     ``solver(K, U, F, nu)`` defaults to ``solve_system`` (direct)."""
     solver = solver or solve_system
+    p1, q11, a1, a2 = {"FE": (1.0, 1.0, None, None), "ME": (1.0, 1.0, 0.5, 0.5), "BE": (1.0, 1.0, 0.0, 1.0),
+                       "Ralston": (2 / 3, 2 / 3, 1 / 4, 3 / 4)}[scheme]       # mech-solver.jl:279-288
     ndofs, nu = om.ndofs, om.nu
     ftol = tol
     om.state_backup()                                                 # StateBk = copy.(State)  :246
@@ -328,8 +331,8 @@ def mech_stage_solver(om: OracleModel, Uex, Fex, nincs=1, tol=0.01, rtol=0.01, r
             if st:
                 syserror, sysmsg = True, f"mount_K status {st}"
                 break
-            dUitr = 1.0 * dUi
-            Rtr = 1.0 * R
+            dUitr = p1 * dUi
+            Rtr = q11 * R
             sok, smsg = solver(K, dUitr, Rtr, nu)
             if not sok:
                 syserror, sysmsg = True, smsg
@@ -340,7 +343,25 @@ def mech_stage_solver(om: OracleModel, Uex, Fex, nincs=1, tol=0.01, rtol=0.01, r
             if st:
                 syserror, sysmsg = True, f"update_state status {st}"
                 break
-            dUi = dUitr
+            if scheme == "FE":
+                dUi = dUitr
+            else:                                                     # corrector step, mech-solver.jl:341-350
+                st, K2 = om.mount_K()
+                if st:
+                    syserror, sysmsg = True, f"mount_K status {st}"
+                    break
+                K = a1 * K + a2 * K2
+                Rc2 = 1.0 * R                                         # solve_system! mutates R[nu+1:end]; R is rebuilt below
+                sok, smsg = solver(K, dUi, Rc2, nu)
+                if not sok:
+                    syserror, sysmsg = True, smsg
+                    break
+                om.state_restore()
+                dUt = dUa + dUi
+                dFin, st = om.update_state(dUt)
+                if st:
+                    syserror, sysmsg = True, f"update_state status {st}"
+                    break
             dUa += dUi
             R[:] = dFex - dFin
             R[nu:] = 0.0

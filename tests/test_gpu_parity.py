@@ -295,6 +295,25 @@ def test_solve_vm_cantilever_fixed_increments():
     assert (model.state["epa"] > 0).sum() == (om.epa > 0).sum() > 0
 
 
+@pytest.mark.parametrize("scheme", ["ME", "BE", "Ralston"])
+def test_solve_predictor_corrector_schemes(scheme):
+    """scheme = :ME / :BE / :Ralston (mech-solver.jl:279-288, corrector :341-350: K = a1*K + a2*K2 through
+    amaru_tangent_save / amaru_tangent_blend) on the vm-3d cantilever: same iteration history and end state as the oracle."""
+    th = 0.05
+
+    def mk():
+        mesh = Mesh(Block([[0, 0, -0.05], [0.05, 1.0, 0.05]], nx=1, ny=12, nz=2, cellshape="HEX20"))
+        return FEModel(mesh, [("bulks", MechSolid, VonMises, dict(E=210e6, nu=0.3, fy=240e3, H=1e5))], MechContext())
+    bcs = [("y==0", NodeBC(uy=0)), ("y==0 && z==0", NodeBC(uz=0)), (f"x=={th/2} && y==0 && z==0", NodeBC(ux=0)),
+           (f"x=={th/2} && y==1 && z==0", NodeBC(uz=-0.02))]
+    status, model, ana, r, Uacc, om = drive_both(mk, [(bcs, 8)], maxits=5, tol=1e-2, rtol=1e-2, scheme=scheme)
+    assert status.success == r["success"]
+    assert len(ana.stats) == r["its"]
+    assert rel(model.U, Uacc) < 1e-7
+    assert rel(model.state["sigma"], om.sig) < 1e-6
+    assert (om.epa > 0).sum() > 0 and (model.state["epa"] > 0).sum() == (om.epa > 0).sum()
+
+
 def test_solve_dp_two_stages_autoinc():
     """reference test/mech/mat/dp.jl: load then unload, IP state carried across stages, autoinc; `.success`."""
     def mk():
