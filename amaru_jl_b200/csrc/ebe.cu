@@ -42,7 +42,8 @@ struct EbeBatch {          // per element batch, colour-sorted element order (sa
     double *d_geo = nullptr;      // [(nd*nd+1)][nipb]: J⁻¹ row-major planes, then coef
     int32_t *d_econn = nullptr;   // [nelem*nn] node | prescribed-dof mask << 28 | ghost << 31
     int32_t *d_einfo = nullptr;   // [nelem] material | (some IP has w != 0) << 30 | (element owned by another rank) << 31
-    int grid = 1;
+    int grid = 1;                 // persistent grid of the DFMA kernel (k_ebe_apply)
+    int grid_mma = 1;             // persistent grid of the DMMA kernel (k_ebe_mma)
 };
 
 struct Ebe {
@@ -51,6 +52,7 @@ struct Ebe {
     double *d_dog = nullptr;      // [nmats][3]: c(1-ν), cν, c(1-2ν)
     int64_t *d_nplastic = nullptr;   // device counter of IPs in flagged elements (for the byte count)
     int64_t nplastic_ip = 0;
+    bool mma = true;              // contractions on the FP64 tensor cores (AMARU_EBE_MMA=0: the DFMA kernel, kept for A/B)
 };
 
 struct EbeArgs {
@@ -477,6 +479,27 @@ __global__ void k_count_flags(int64_t n, int nip, const int32_t *__restrict__ f,
     if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);   // integer count: order-independent
 }
 
+#include "ebe_mma.cuh"
+
+template <int NN, int ND, int NIP>
+int ebe_mma_configure(amaru_model *m) {
+    int occ0 = 0, occ1 = 0;
+    const size_t s0 = MmaLayout<NN, ND, NIP, false>::bytes, s1 = MmaLayout<NN, ND, NIP, true>::bytes;
+    auto k0 = k_ebe_mma<NN, ND, NIP, false>;
+    auto k1 = k_ebe_mma<NN, ND, NIP, true>;
+    CUDA_CHECK(cudaFuncSetAttribute(k0, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s0));
+    CUDA_CHECK(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s1));
+    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ0, k0, 128, s0));
+    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ1, k1, 128, s1));
+    return m->nsm * std::max(1, std::min(std::min(occ0, occ1), 8));
+}
+
+template <int NN, int ND, int NIP>
+void ebe_mma_launch(amaru_model *m, const EbeArgs &a, int grid, bool mass) {
+    if (mass) k_ebe_mma<NN, ND, NIP, true><<<grid, 128, MmaLayout<NN, ND, NIP, true>::bytes, m->stream>>>(a);
+    else k_ebe_mma<NN, ND, NIP, false><<<grid, 128, MmaLayout<NN, ND, NIP, false>::bytes, m->stream>>>(a);
+}
+
 template <int NN, int ND, int NIP, int TA, int NT>
 int ebe_configure(amaru_model *m) {
     int occ0 = 0, occ1 = 0;
@@ -510,6 +533,7 @@ void amaru_ebe_setup(amaru_model *m) {
     m->op_ebe = !(op && std::strcmp(op, "csr") == 0);
     Ebe *E = new Ebe();
     m->ebe = E;
+    if (const char *e = getenv("AMARU_EBE_MMA")) E->mma = std::atoi(e) != 0;
     E->b.resize(m->batches.size());
     std::vector<double> dog((size_t)m->nmats * 3);
     {
@@ -548,11 +572,11 @@ void amaru_ebe_setup(amaru_model *m) {
         const int g = (int)std::min<int64_t>((nipb + 127) / 128, (int64_t)m->nsm * 16);
 #define GEO(NN, ND, NIP) k_ebe_geometry<NN, ND, NIP><<<g, 128, 0, m->stream>>>(b.nelem, b.d_conn, m->d_coords, b.d_dNdR, b.d_w, m->th, eb.d_geo, nipb)
         switch (b.shape) {
-        case AMARU_SHAPE_QUAD4: GEO(4, 2, 4); eb.grid = ebe_configure<4, 2, 4, 2, EBE_NT>(m); break;
-        case AMARU_SHAPE_QUAD8: GEO(8, 2, 4); eb.grid = ebe_configure<8, 2, 4, 4, EBE_NT>(m); break;
-        case AMARU_SHAPE_HEX8: GEO(8, 3, 8); eb.grid = ebe_configure<8, 3, 8, 2, EBE_NT>(m); break;
-        case AMARU_SHAPE_HEX20: GEO(20, 3, 8); eb.grid = ebe_configure<20, 3, 8, 5, EBE_NT>(m); break;
-        case AMARU_SHAPE_TET10: GEO(10, 3, 4); eb.grid = ebe_configure<10, 3, 4, 5, EBE_NT>(m); break;
+        case AMARU_SHAPE_QUAD4: GEO(4, 2, 4); eb.grid = ebe_configure<4, 2, 4, 2, EBE_NT>(m); eb.grid_mma = ebe_mma_configure<4, 2, 4>(m); break;
+        case AMARU_SHAPE_QUAD8: GEO(8, 2, 4); eb.grid = ebe_configure<8, 2, 4, 4, EBE_NT>(m); eb.grid_mma = ebe_mma_configure<8, 2, 4>(m); break;
+        case AMARU_SHAPE_HEX8: GEO(8, 3, 8); eb.grid = ebe_configure<8, 3, 8, 2, EBE_NT>(m); eb.grid_mma = ebe_mma_configure<8, 3, 8>(m); break;
+        case AMARU_SHAPE_HEX20: GEO(20, 3, 8); eb.grid = ebe_configure<20, 3, 8, 5, EBE_NT>(m); eb.grid_mma = ebe_mma_configure<20, 3, 8>(m); break;
+        case AMARU_SHAPE_TET10: GEO(10, 3, 4); eb.grid = ebe_configure<10, 3, 4, 5, EBE_NT>(m); eb.grid_mma = ebe_mma_configure<10, 3, 4>(m); break;
         default: throw AmaruError{AMARU_ERR_UNSUPPORTED, "ebe: unsupported shape"};
         }
 #undef GEO
@@ -638,6 +662,20 @@ void amaru_ebe_apply(amaru_model *m, const double *x, double *y, int mask, int d
             a.e_begin = b.color_off[c];
             a.e_end = b.color_off[c + 1];
             a.last = il == nl;
+            if (E->mma) {   // 4 warps per CTA, 8 elements per warp and group
+                const int grid = (int)std::min<int64_t>((n + 31) / 32, eb.grid_mma);
+                switch (b.shape) {
+                case AMARU_SHAPE_QUAD4: ebe_mma_launch<4, 2, 4>(m, a, grid, mass); break;
+                case AMARU_SHAPE_QUAD8: ebe_mma_launch<8, 2, 4>(m, a, grid, mass); break;
+                case AMARU_SHAPE_HEX8: ebe_mma_launch<8, 3, 8>(m, a, grid, mass); break;
+                case AMARU_SHAPE_HEX20: ebe_mma_launch<20, 3, 8>(m, a, grid, mass); break;
+                case AMARU_SHAPE_TET10: ebe_mma_launch<10, 3, 4>(m, a, grid, mass); break;
+                default: throw AmaruError{AMARU_ERR_UNSUPPORTED, "ebe: unsupported shape"};
+                }
+                m->launches++;
+                a.first = 0;
+                continue;
+            }
             const int epb = EBE_NT / b.nip;
             const int grid = (int)std::min<int64_t>((n + epb - 1) / epb, eb.grid);
             switch (b.shape) {
@@ -667,6 +705,16 @@ int64_t amaru_ebe_bytes(const amaru_model *m) {
 
 const char *amaru_ebe_kernel(const amaru_model *m) {
     if (m->batches.empty()) return "k_ebe_apply";
+    const Ebe *E = static_cast<const Ebe *>(m->ebe);
+    if (E && E->mma) {
+        switch (m->batches[0].shape) {
+        case AMARU_SHAPE_QUAD4: return "k_ebe_mma<4,2,4>";
+        case AMARU_SHAPE_QUAD8: return "k_ebe_mma<8,2,4>";
+        case AMARU_SHAPE_HEX8: return "k_ebe_mma<8,3,8>";
+        case AMARU_SHAPE_HEX20: return "k_ebe_mma<20,3,8>";
+        case AMARU_SHAPE_TET10: return "k_ebe_mma<10,3,4>";
+        }
+    }
     switch (m->batches[0].shape) {
     case AMARU_SHAPE_QUAD4: return "k_ebe_apply<4,2,4,2>";
     case AMARU_SHAPE_QUAD8: return "k_ebe_apply<8,2,4,4>";

@@ -95,7 +95,7 @@ def ip_coords(shape, coords, nodes, ndim):
 def entity_forces(shape, C, ndim, th, key, vals):
     """One call of mech_boundary_forces (facet) / mech_solid_body_forces (cell): C (nn, ndim), vals (nip,) -> (nn, ndim)."""
     ips = quadrature(shape)
-    facet = shape_dim(shape) == ndim - 1
+    facet = shape_dim(shape) < ndim        # faces, 2D edges, and the 3D edges of EdgeBC (qx qy qz; th = 1.0, distributed.jl:95)
     F = np.zeros((C.shape[0], ndim))
     for q in range(ips.shape[0]):
         R, w = ips[q, :3], ips[q, 3]
