@@ -419,6 +419,7 @@ def test_symmetric_storage_spmv_matches_full_storage(shape, n, precond, monkeypa
     eqid, nu, setup = model.configure_dofs(bcs)
     Uex, Fex = model.get_bc_vals(eqid, setup)
     out = {}
+    monkeypatch.setenv("AMARU_OPERATOR", "csr")   # the assembled-matrix CG operators (the default is the matrix-free one)
     for sym in ("1", "0"):
         monkeypatch.setenv("AMARU_SPMV_SYM", sym)
         dm = L.DeviceModel(model.flatten(), eqid, eqid.size, nu)
