@@ -55,6 +55,28 @@ void amaru_build_pattern(int64_t nrows, int nbatches, const int *nn, const int64
                          const std::vector<int64_t> &adj, HostPattern &pat);
 int amaru_host_threads();
 
+// ---- patch plan of the matrix-free operator (patches.cpp; consumed by ebe.cu) ---------------------------------
+constexpr uint32_t PN_NODE = 0x07ffffffu;    // patch-node entry: node | first-touch << 27 | prescribed-dof mask << 28 | ghost << 31
+constexpr uint32_t PN_FIRST = 1u << 27;      // no earlier patch (in processing order) lists the node: y starts from zero
+constexpr uint32_t PN_GHOST = 1u << 31;      // row of a neighbour rank: never stored
+struct PatchPlan {
+    int pe = 64, maxpn = 0, nn = 0;
+    int64_t nslots = 0;                 // 8 element slots per group, groups numbered patch by patch
+    int npatch = 0, ncolors = 0, maxgroups = 0;
+    double fill = 0.0;                  // elements / slots
+    std::vector<int32_t> slot_elem;     // [nslots] colour-sorted element of the slot, -1 = empty
+    std::vector<int32_t> desc;          // [npatch][8]: first group, groups, first node entry, nodes, first dep, deps, 0, 0
+    std::vector<uint32_t> pnodes;       // node entries, ascending node id inside a patch
+    std::vector<uint16_t> lane_ids;     // [group][word][lane][4]: patch-local node ids in DMMA fragment order (ebe_patch.cuh)
+    std::vector<int32_t> deps;          // lower-coloured patches sharing a node with the patch
+};
+inline int amaru_patch_id_words(int nn) { return ((nn + 3) / 4 + 2 * ((nn + 7) / 8) + 3) / 4; }
+// elements per patch, node capacity of the shared-memory bricks, brick size in cells
+void amaru_patch_shape_params(int shape, int &pe, int &maxpn, int brick[3]);
+void amaru_build_patches(int nn, int nd, int pe, int maxpn, const int brick[3], int64_t nelem, const int32_t *sconn,
+                         const std::vector<int64_t> &color_off, int64_t nnodes, int64_t nowned, const double *coords,
+                         const uint8_t *fixed, std::vector<uint8_t> &touched, PatchPlan &out);
+
 // ---- device model ------------------------------------------------------------------------------------------
 struct Batch {
     int shape = 0, nn = 0, nd = 0, nip = 0;
@@ -254,6 +276,8 @@ void amaru_ebe_destroy(amaru_model *m);
 void amaru_ebe_refresh(amaru_model *m);                               // tangent planes <- current IP state
 void amaru_ebe_set_owned(amaru_model *m, int batch, const uint8_t *h_owned_sorted);
 void amaru_ebe_apply(amaru_model *m, const double *x, double *y, int mask, int dot, int check_done, int finalize);
+void amaru_ebe_begin(amaru_model *m);                                 // before a solve: fresh epochs / tickets of the patch form
+void amaru_ebe_patch_stats(const amaru_model *m, int64_t *npatch, int64_t *nslots, int64_t *pnodes, int64_t *pnodes_loaded);
 int64_t amaru_ebe_bytes(const amaru_model *m);
 const char *amaru_ebe_kernel(const amaru_model *m);
 

@@ -314,6 +314,7 @@ static void spmv_dot(amaru_model *m, const double *A, const double *x, double *y
 double amaru_operator_product(amaru_model *m, int masked) {
     amaru_spmv_sym_refresh(m);
     CUDA_CHECK(cudaMemsetAsync(m->d_scal, 0, sizeof(CgScalars), m->stream));
+    amaru_ebe_begin(m);
     if (m->nranks > 1) amaru_halo_exchange(m, m->d_p);
     if (masked) {
         const bool prof = m->profiling;
@@ -461,6 +462,7 @@ void amaru_zero_free(amaru_model *m, double *x) {
 void amaru_pcg_solve(amaru_model *m, double rtol, int maxit, int precond, SolveInfo &info) {
     build_preconditioner(m, precond);
     amaru_spmv_sym_refresh(m);   // upper blocks of the current system matrix for the CG products
+    amaru_ebe_begin(m);
     const int64_t nloc = m->nowned * m->nd;
     amaru_zero_free(m, m->d_x);   // the first product must be K*[0;U2]
     const bool bj = precond == AMARU_PRECOND_BLOCK_JACOBI;
@@ -547,6 +549,7 @@ void amaru_time_cg_kernel(amaru_model *m, int kind, int precond, int reps) {
     build_preconditioner(m, precond);
     amaru_spmv_sym_refresh(m);
     CUDA_CHECK(cudaMemsetAsync(m->d_scal, 0, sizeof(CgScalars), m->stream));   // done = 0, alpha = beta = 0
+    amaru_ebe_begin(m);
     const int gn = node_grid(m, m->nowned);
     const int64_t nloc = m->nowned * m->nd;
     const bool prof = m->profiling;

@@ -90,6 +90,7 @@ SYMBOLS = {
     "amaru_set_device_vectors": (C.c_int, [_vp, _dp, _dp, C.c_char_p, C.c_int]),
     "amaru_time_kernel": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _dp, C.c_char_p, C.c_int]),
     "amaru_set_operator": (C.c_int, [_vp, C.c_int]),
+    "amaru_patch_plan_check": (C.c_int, [C.c_int, C.c_int64, C.c_int64, _vp, C.c_int64, _vp, _vp]),
     "amaru_operator_apply": (C.c_int, [_vp, _dp, _dp, C.c_int, _dp, C.c_char_p, C.c_int]),
     "amaru_set_profiling": (C.c_int, [_vp, C.c_int]),
     "amaru_get_profile": (C.c_int, [_vp, _dp, _i64p]),

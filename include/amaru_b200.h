@@ -307,6 +307,12 @@ int amaru_get_profile(amaru_model *m, double *spmv_ms_total, int64_t *spmv_launc
 int64_t amaru_spmv_bytes(const amaru_model *m);
 /* name of the SpMV kernel the CG loop of this handle launches (for the bench's roofline record) */
 const char *amaru_spmv_kernel(const amaru_model *m);
+/* Host-only diagnostic of the matrix-free operator's patch plan (patches.cpp): builds the plan amaru_create would build
+ * for one batch of `shape` cells and checks its invariants (every element in exactly one slot, groups node-disjoint,
+ * patch-local ids consistent, first-touch / ghost flags, dependencies = every earlier patch sharing a node).  Returns 0 or
+ * the number of the violated rule; stats[6] = patches, patch colours, slot fill, slots, max groups per patch, dependencies. */
+int amaru_patch_plan_check(int shape, int64_t nnodes, int64_t nowned, const double *coords, int64_t nelem,
+                           const int32_t *conn, double *stats);
 /* number of kernels launched by this handle since creation (the bench's gpu_launches claim) */
 int64_t amaru_launch_count(const amaru_model *m);
 

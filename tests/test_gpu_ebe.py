@@ -14,6 +14,17 @@ from test_gpu_parity import MATS, SHAPES, clamp_bcs, make_model, pair, rel
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True, params=["patch", "colour"])
+def operator_form(request, monkeypatch):
+    """Every test runs on both forms of the matrix-free operator: k_ebe_patch (x / y of a patch in shared memory; forced here
+    even where the small test meshes fill the patch slots poorly) and the colour-ordered k_ebe_mma."""
+    if request.param == "patch":
+        monkeypatch.setenv("AMARU_EBE_PATCH_MINFILL", "0")
+    else:
+        monkeypatch.setenv("AMARU_EBE_PATCH", "0")
+    return request.param
+
+
 def plastic_state(model, om, dm, eqid, mat, seed=3):
     rng = np.random.default_rng(seed)
     scale = {"le": 1e-3, "vm": 4e-3, "vm0": 4e-3, "dp": 5e-3}[mat]
@@ -96,6 +107,42 @@ def test_solve_is_operator_independent(shape, n, mat, precond):
     U, F = Uex.copy(), Fex.copy()
     ok, _ = O.solve_system(K, U, F, nu)
     assert ok and rel(out["ebe"][0], U) < 1e-8
+    dm.close()
+
+
+def test_operator_form_is_the_requested_one(operator_form):
+    model = make_model("HEX20", 2, "le")
+    om, dm, eqid, nu, _ = pair(model, clamp_bcs(model))
+    assert dm.spmv_kernel.startswith("k_ebe_patch" if operator_form == "patch" else "k_ebe_mma")
+    dm.close()
+
+
+@pytest.mark.parametrize("shape,n", [("HEX20", 12), ("HEX20", 9), ("TET10", 8), ("HEX8", 13), ("QUAD8", 40)])
+def test_many_patches_match_csr_and_repeat_bitwise(shape, n):
+    """Enough patches (27 ... 100) that several warps and CTAs work concurrently and wait on each other's rows: the product
+    equals the block-CSR product of the assembled tangent (plastic state) and repeats bit for bit."""
+    model = make_model(shape, n, "vm0" if shape != "QUAD8" else "vm", jitter=0.1, seed=5)
+    bcs = clamp_bcs(model)
+    eqid, nu, setup = model.configure_dofs(bcs)
+    dm = L.DeviceModel(model.flatten(), eqid, eqid.size, nu)
+    rng = np.random.default_rng(8)
+    dm.state_backup()
+    dm.update_state(rng.uniform(-1, 1, eqid.size) * 6e-3)
+    dm.assemble_K()
+    x = rng.uniform(-1, 1, eqid.size)
+    xm = x.copy()
+    xm[nu:] = 0.0
+    dm.set_operator("csr")
+    yc, _ = dm.operator_apply(x, masked=False)
+    ycm, pqc = dm.operator_apply(xm, masked=True)
+    dm.set_operator("ebe")
+    y0, _ = dm.operator_apply(x, masked=False)
+    ym0, pq0 = dm.operator_apply(xm, masked=True)
+    assert rel(y0, yc) < 1e-12 and rel(ym0, ycm) < 1e-12 and abs(pq0 - pqc) <= 1e-12 * abs(pqc)
+    for _ in range(5):
+        y, _ = dm.operator_apply(x, masked=False)
+        ym, pq = dm.operator_apply(xm, masked=True)
+        assert np.array_equal(y, y0) and np.array_equal(ym, ym0) and pq == pq0
     dm.close()
 
 
