@@ -157,10 +157,19 @@ __global__ void __launch_bounds__(128, 2) k_ebe_patch(PatchArgs p) {
     // Tickets are taken two patches ahead (the atomic's round trip and the descriptor / node-list loads of the next patch
     // hide behind the current one).  A warp works through its tickets in increasing order, so the holder of the smallest
     // unfinished ticket is always working on it: still no deadlock.
-    auto take = [&]() -> int {
+    auto take_raw = [&]() -> int {                       // the atomic's result stays in lane 0 until it is needed
         int t = 0;
         if (lane == 0) t = (int)atomicAdd(p.ticket, 1u);
-        return __shfl_sync(0xffffffffu, t, 0);
+        return t;
+    };
+    constexpr int NPL = (MAXPN + 31) / 32;               // node entries per lane
+    uint32_t pn[NPL], pq_[NPL];                          // entries of the current / of the next patch (registers)
+    auto load_entries = [&](uint32_t (&e)[NPL], int first, int count) {
+#pragma unroll
+        for (int u = 0; u < NPL; u++) {
+            const int i = u * 32 + lane;
+            e[u] = i < count ? __ldg(p.pnodes + first + i) : (PN_GHOST | PN_FIRST);
+        }
     };
     auto load_desc = [&](int t, int4 &a, int4 &b) {
         if (t < p.npatch) {
@@ -168,35 +177,39 @@ __global__ void __launch_bounds__(128, 2) k_ebe_patch(PatchArgs p) {
             b = __ldg(reinterpret_cast<const int4 *>(p.desc) + 2 * t + 1);
         }
     };
-    int pt = take(), pt1 = take();
+    auto prefetch_next = [&]() {
+#pragma unroll
+        for (int u = 0; u < NPL; u++) {
+            if (!(pq_[u] & PN_GHOST) || !(pq_[u] & PN_FIRST)) {   // (PN_GHOST | PN_FIRST) marks the padding past the list
+                const int64_t o = (int64_t)(pq_[u] & PN_NODE) * ND;
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(p.x + o));
+                if (!(pq_[u] & (PN_FIRST | PN_GHOST))) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.y + o));
+            }
+        }
+    };
+    int pt = __shfl_sync(0xffffffffu, take_raw(), 0), pt1 = __shfl_sync(0xffffffffu, take_raw(), 0);
     int4 d0 = make_int4(0, 0, 0, 0), d1 = d0, n0 = d0, n1 = d0;
     load_desc(pt, d0, d1);
+    if (pt < p.npatch) load_entries(pn, d0.z, d0.w);
     while (pt < p.npatch) {
-        const int grp0 = d0.x, ngrp = d0.y, node0 = d0.z, nnode = d0.w, dep0 = d1.x, ndep = d1.y;
-        const int pt2 = take();                          // consumed at the end of this patch
+        const int grp0 = d0.x, ngrp = d0.y, nnode = d0.w, dep0 = d1.x, ndep = d1.y;
+        const int pt2_raw = take_raw();                  // consumed at the end of this patch
         load_desc(pt1, n0, n1);                          // consumed after the first group
+        int stage_next = pt1 < p.npatch ? 0 : 2;         // next patch: 0 entries not loaded, 1 loaded, 2 prefetched
         int ei = __ldg(p.einfo + (int64_t)grp0 * 8 + er);
         int ei1 = ngrp > 1 ? __ldg(p.einfo + (int64_t)(grp0 + 1) * 8 + er) : EP_EMPTY;
         load_geo(grp0);                                  // in flight while the bricks are being filled
         // ---- x brick (does not depend on other patches)
-        for (int i0 = 0; i0 < nnode; i0 += 128) {        // 4 node entries per lane in flight
-            uint32_t e4[4];
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
-                const int i = i0 + u * 32 + lane;
-                e4[u] = i < nnode ? __ldg(p.pnodes + node0 + i) : 0u;
-            }
+        for (int u = 0; u < NPL; u++) {                  // the entries are in registers since the previous patch
+            const int i = u * 32 + lane;
+            if (i < nnode) {
+                sP[i] = pn[u];
+                const double *src = p.x + (int64_t)(pn[u] & PN_NODE) * ND;
+                const uint32_t dst = (uint32_t)__cvta_generic_to_shared(sX + i * ND);
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
-                const int i = i0 + u * 32 + lane;
-                if (i < nnode) {
-                    sP[i] = e4[u];
-                    const double *src = p.x + (int64_t)(e4[u] & PN_NODE) * ND;
-                    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(sX + i * ND);
-#pragma unroll
-                    for (int c = 0; c < ND; c++)
-                        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + c * 8u), "l"(src + c) : "memory");
-                }
+                for (int c = 0; c < ND; c++)
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + c * 8u), "l"(src + c) : "memory");
             }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
@@ -214,12 +227,12 @@ __global__ void __launch_bounds__(128, 2) k_ebe_patch(PatchArgs p) {
             if (!__all_sync(0xffffffffu, ok) && lane == 0) p.scal->done = 3;   // a neighbour never finished: report, do not hang
         }
         __syncwarp();
-        for (int i0 = 0; i0 < nnode; i0 += 128) {        // 4 nodes per lane in flight
+#pragma unroll
+        for (int u0 = 0; u0 < NPL; u0 += 4) {            // 4 nodes per lane in flight
             double v[4][ND];
 #pragma unroll
             for (int u = 0; u < 4; u++) {
-                const int i = i0 + u * 32 + lane;
-                const uint32_t ent = i < nnode ? sP[i] : PN_FIRST;
+                const uint32_t ent = u0 + u < NPL ? pn[u0 + u < NPL ? u0 + u : 0] : (PN_FIRST | PN_GHOST);
                 const bool ld = !(ent & (PN_FIRST | PN_GHOST));
                 const double *src = p.y + (int64_t)(ent & PN_NODE) * ND;
 #pragma unroll
@@ -227,8 +240,8 @@ __global__ void __launch_bounds__(128, 2) k_ebe_patch(PatchArgs p) {
             }
 #pragma unroll
             for (int u = 0; u < 4; u++) {
-                const int i = i0 + u * 32 + lane;
-                if (i < nnode) {
+                const int i = (u0 + u) * 32 + lane;
+                if (u0 + u < NPL && i < nnode) {
 #pragma unroll
                     for (int c = 0; c < ND; c++) sY[i * ND + c] = v[u][c];
                 }
@@ -300,23 +313,12 @@ __global__ void __launch_bounds__(128, 2) k_ebe_patch(PatchArgs p) {
                 ei = ei1;
                 ei1 = g + 2 < ngrp ? __ldg(p.einfo + (int64_t)(grp0 + g + 2) * 8 + er) : EP_EMPTY;
             }
-            if (g == 0 && pt1 < p.npatch) {              // next patch: pull its node list, x and y towards L2
-                for (int i0 = 0; i0 < n0.w; i0 += 128) {
-                    uint32_t e4[4];
-#pragma unroll
-                    for (int u = 0; u < 4; u++) {
-                        const int i = i0 + u * 32 + lane;
-                        e4[u] = i < n0.w ? __ldg(p.pnodes + n0.z + i) : PN_GHOST;
-                    }
-#pragma unroll
-                    for (int u = 0; u < 4; u++) {
-                        if (i0 + u * 32 + lane < n0.w) {
-                            const int64_t o = (int64_t)(e4[u] & PN_NODE) * ND;
-                            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.x + o));
-                            if (!(e4[u] & (PN_FIRST | PN_GHOST))) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.y + o));
-                        }
-                    }
-                }
+            if (stage_next == 1) {                       // next patch: x and y towards L2 (entries arrived a group ago)
+                prefetch_next();
+                stage_next = 2;
+            } else if (stage_next == 0) {                // next patch: node entries -> registers (its descriptor arrived)
+                load_entries(pq_, n0.z, n0.w);
+                stage_next = 1;
             }
             // ---- contraction 2: F[i][n] += A(S; step (k,h), m-tile i) · B3[step][n]; the accumulators start from the y brick
             double F[ND][NT3][2];
@@ -372,8 +374,12 @@ __global__ void __launch_bounds__(128, 2) k_ebe_patch(PatchArgs p) {
             __threadfence();
             st_release_gpu_u32(p.done + pt, epoch);
         }
-        pt = pt1; pt1 = pt2;
+        if (stage_next == 0) load_entries(pq_, n0.z, n0.w);   // patches of one group
+        pt = pt1;
+        pt1 = __shfl_sync(0xffffffffu, pt2_raw, 0);
         d0 = n0; d1 = n1;
+#pragma unroll
+        for (int u = 0; u < NPL; u++) pn[u] = pq_[u];
     }
 
     // ---- last CTA: p·Ap in patch order, CG scalars, reset of the ticket counter, epoch of this application

@@ -15,6 +15,7 @@
 #include <cstring>
 
 #include "amaru_internal.h"
+#include "p2p.cuh"
 
 namespace {
 
@@ -109,52 +110,7 @@ __global__ void k_pack(int64_t n, int nd, const int32_t *__restrict__ nodes, con
 // finished reading epoch e.  Ghost entries are rewritten only after an all-reduce that every rank enters after the
 // product that read them.  Every wait is bounded (timeout_ns of %globaltimer): a rank that gives up raises the abort flag
 // in every window, all spinning kernels leave, later ones return at once, and the host reports AMARU_ERR_COMM.
-constexpr int P2P_MAXR = 16;
-struct P2PWin {
-    double slot[2][P2P_MAXR][4];
-    unsigned long long sflag[2][P2P_MAXR];
-    unsigned long long hflag[P2P_MAXR];
-    unsigned long long halo_epoch, scal_epoch;   // completed epochs of this rank
-    int abort;
-};
-struct P2PDev {
-    int rank, nranks;
-    unsigned long long timeout_ns;
-    P2PWin *win[P2P_MAXR];
-};
-
-__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
-    unsigned long long v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ unsigned long long global_ns() {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    return t;
-}
-// wait until *flag >= epoch; false (and the abort flag raised everywhere) when the budget ran out or a peer aborted
-__device__ bool p2p_wait(const P2PDev &pd, const unsigned long long *flag, unsigned long long epoch) {
-    P2PWin *me = pd.win[pd.rank];
-    const unsigned long long t0 = global_ns();
-    unsigned int it = 0;
-    while (ld_acquire_sys(flag) < epoch) {
-        if ((++it & 255u) == 0) {
-            const bool late = global_ns() - t0 > pd.timeout_ns;
-            if (late || *reinterpret_cast<volatile int *>(&me->abort)) {
-                for (int r = 0; r < pd.nranks; r++) *reinterpret_cast<volatile int *>(&pd.win[r]->abort) = 1;
-                __threadfence_system();
-                return false;
-            }
-        }
-        __nanosleep(20);
-    }
-    return true;
-}
-
+// (window layout and wait / release primitives: p2p.cuh)
 // op 0: sum, 1: max
 __global__ void k_p2p_allreduce(P2PDev pd, double *vals, int n, int op) {
     const int lane = threadIdx.x;
