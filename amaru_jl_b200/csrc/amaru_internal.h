@@ -275,7 +275,7 @@ void amaru_ebe_setup(amaru_model *m);
 void amaru_ebe_destroy(amaru_model *m);
 void amaru_ebe_refresh(amaru_model *m);                               // tangent planes <- current IP state
 void amaru_ebe_set_owned(amaru_model *m, int batch, const uint8_t *h_owned_sorted);
-void amaru_ebe_apply(amaru_model *m, const double *x, double *y, int mask, int dot, int check_done, int finalize);
+void amaru_ebe_apply(amaru_model *m, const double *x, double *y, int mask, int dot, int check_done, int finalize, int fused = 0);
 void amaru_ebe_begin(amaru_model *m);                                 // before a solve: fresh epochs / tickets of the patch form
 void amaru_ebe_patch_stats(const amaru_model *m, int64_t *npatch, int64_t *nslots, int64_t *pnodes, int64_t *pnodes_loaded);
 int64_t amaru_ebe_bytes(const amaru_model *m);
@@ -291,5 +291,8 @@ void amaru_comm_setup(amaru_model *m, int nneigh, const int32_t *neigh_rank, con
 void amaru_comm_destroy(amaru_model *m);
 bool amaru_comm_is_p2p(const amaru_model *m);                        // CG-loop exchanges run as peer-memory kernels
 void amaru_comm_check(amaru_model *m);                               // throws AMARU_ERR_COMM if a peer-memory wait timed out
+bool amaru_comm_fused(const amaru_model *m);                         // exchanges of the CG loop may be folded into its kernels (p2p.cuh)
+void amaru_halo_push(amaru_model *m, double *d_v);                   // producer half of a halo exchange of p (fused loop)
+bool amaru_ebe_fusable(const amaru_model *m);                        // the operator kernels carry the hooks of the fused multi-GPU loop
 void amaru_p2p_connect_direct(amaru_model *const *parts, int n);    // in-process peers (amaru_create with ngpus > 1)
 void amaru_recovery_destroy(amaru_model *m);   // recovery.cu

@@ -26,6 +26,7 @@
 #include <cstring>
 
 #include "materials.cuh"
+#include "p2p.cuh"
 #include "reduce.cuh"
 
 namespace {
@@ -92,6 +93,8 @@ struct EbeArgs {
     double *partial;
     CgScalars *scal;
     int dot, first, last, finalize, check_done;
+    int fused;              // multi-GPU fused CG loop (p2p.cuh): first launch waits for the halo of x, last launch pushes p.Ap
+    P2PFused fz;
 };
 
 template <int NN, int ND, int NIP, int TA, bool MASS, int NT>
@@ -648,6 +651,12 @@ void ebe_patch_setup(amaru_model *m, Ebe *E, Batch &b, EbeBatch &eb, const std::
     double minfill = 0.6;
     if (const char *e = getenv("AMARU_EBE_PATCH_MINFILL")) minfill = std::atof(e);
     if (P.fill < minfill) return;
+    // Patches of one 2x2x2 neighbourhood run one after the other (8 patch colours), so an application costs at least 8 patch
+    // times however many warps are idle: below ~8 patches per resident warp the colour-ordered form (one 8-element group per
+    // warp step, no serial chain) is faster — the strong-scaling regime of the multi-GPU runs.
+    int64_t minpatch = (int64_t)8 * m->nsm * 8;
+    if (const char *e = getenv("AMARU_EBE_PATCH_MINPATCH")) minpatch = std::atoll(e);
+    if (P.npatch < minpatch) return;
     touched.swap(t2);
     eb.patch = true;
     eb.npatch = P.npatch;
@@ -856,7 +865,7 @@ void amaru_ebe_refresh(amaru_model *m) {
 }
 
 // y = (sysA·K + sysB·M) x on the owned rows (+ p·Ap and CG scalar finalisation when dot != 0); x needs valid ghost entries
-void amaru_ebe_apply(amaru_model *m, const double *x, double *y, int mask, int dot, int check_done, int finalize) {
+void amaru_ebe_apply(amaru_model *m, const double *x, double *y, int mask, int dot, int check_done, int finalize, int fused) {
     Ebe *E = ebe_of(m);
     AMARU_REQUIRE(E != nullptr, AMARU_ERR_ARG, "ebe: operator not set up");
     const bool mass = m->sysB != 0.0;
@@ -876,6 +885,9 @@ void amaru_ebe_apply(amaru_model *m, const double *x, double *y, int mask, int d
     a.x = x; a.y = y; a.mask = mask; a.nmats = m->nmats;
     a.partial = m->d_partial; a.scal = m->d_scal; a.dot = dot; a.finalize = finalize; a.check_done = check_done;
     a.first = 1;
+    a.fused = fused && E->mma;
+    if (a.fused) a.fz = amaru_comm_fused_args(m);
+    else std::memset(&a.fz, 0, sizeof(a.fz));
     for (size_t i = 0; i < m->batches.size(); i++) {
         Batch &b = m->batches[i];
         EbeBatch &eb = E->b[i];
@@ -888,6 +900,9 @@ void amaru_ebe_apply(amaru_model *m, const double *x, double *y, int mask, int d
             pa.sa = m->sysA; pa.sb = m->sysB; pa.x = x; pa.y = y; pa.mask = mask; pa.npatch = eb.npatch;
             pa.ticket = eb.d_sync; pa.epoch = eb.d_sync + 1; pa.done = eb.d_sync + 2; pa.counter = &m->d_scal->counter[0];
             pa.epatch = eb.d_epatch; pa.scal = m->d_scal; pa.dot = dot; pa.finalize = finalize; pa.check_done = check_done;
+            pa.fused = fused;
+            if (fused) pa.fz = amaru_comm_fused_args(m);
+            else std::memset(&pa.fz, 0, sizeof(pa.fz));
             il++;
             pa.first = a.first;
             pa.last = il == nl;
@@ -942,6 +957,12 @@ void amaru_ebe_apply(amaru_model *m, const double *x, double *y, int mask, int d
         }
     }
     CUDA_CHECK(cudaGetLastError());
+}
+
+// the DMMA forms of the operator (patch and colour-ordered) carry the hooks of the fused multi-GPU loop
+bool amaru_ebe_fusable(const amaru_model *m) {
+    const Ebe *E = static_cast<const Ebe *>(m->ebe);
+    return E && E->mma;
 }
 
 // Start of a solve / measurement: ticket counters cleared and a fresh range of application epochs, so that a kernel that gave

@@ -50,7 +50,9 @@ struct MmaLayout {
     static constexpr int NW = EW * NN;                            // econn entries of one stage
     static constexpr int WARPS = 4;
     static constexpr size_t tab_doubles = (size_t)(KS2 * NT2 + KS3 * NT3) * 32;
-    static constexpr size_t bytes = tab_doubles * 8 + (size_t)WARPS * 2 * XW * 8 + (size_t)WARPS * 2 * NW * 4 + 3 * EBE_SMATS * 8;
+    static constexpr int YW = XW + 8;                             // y stage of one group (padded node columns read past a row)
+    static constexpr size_t bytes = tab_doubles * 8 + (size_t)WARPS * 2 * XW * 8 + (size_t)WARPS * 2 * YW * 8 +
+                                    (size_t)WARPS * 2 * NW * 4 + 3 * EBE_SMATS * 8;
     static_assert(NIP == 4 || NIP == 8, "lane <-> integration point mapping needs 4 or 8 integration points");
 };
 
@@ -123,14 +125,15 @@ __global__ void __launch_bounds__(128) k_ebe_mma(EbeArgs p) {
     if (p.check_done && p.scal->done) return;
     using L = MmaLayout<NN, ND, NIP, MASS>;
     constexpr int EW = L::EW, IPL = L::IPL, KS2 = L::KS2, NT2 = L::NT2, NG2 = L::NG2, KS3 = L::KS3, NT3 = L::NT3, RSX = L::RSX,
-                  XW = L::XW, NW = L::NW, NT = 128;
+                  XW = L::XW, YW = L::YW, NW = L::NW, NT = 128;
     constexpr int NLD = (NW + 31) / 32;                  // econn entries per lane and group
     extern __shared__ __align__(16) double msm[];
     double *sB2 = msm;                                   // [KS2][NT2][32]
     double *sB3 = sB2 + KS2 * NT2 * 32;                  // [KS3][NT3][32]
     double *sDog = sB3 + KS3 * NT3 * 32;                 // [EBE_SMATS][3]
     double *sXall = sDog + 3 * EBE_SMATS;                // [WARPS][2][ND][EW][RSX]
-    int32_t *sNall = reinterpret_cast<int32_t *>(sXall + L::WARPS * 2 * XW);   // [WARPS][2][EW][NN]
+    double *sYall = sXall + L::WARPS * 2 * XW;           // [WARPS][2][ND][EW][RSX] (+ pad): y of the group's nodes
+    int32_t *sNall = reinterpret_cast<int32_t *>(sYall + L::WARPS * 2 * YW);   // [WARPS][2][EW][NN]
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int er = lane >> 2, j = lane & 3;              // this lane's element of the group / position in the quad
 
@@ -163,8 +166,16 @@ __global__ void __launch_bounds__(128) k_ebe_mma(EbeArgs p) {
     if (smats)
         for (int i = tid; i < 3 * p.nmats; i += NT) sDog[i] = p.dog[i];
     double *sX = sXall + wid * 2 * XW;
+    double *sY = sYall + wid * 2 * YW;
     int32_t *sN = sNall + wid * 2 * NW;
     for (int i = lane; i < 2 * XW; i += 32) sX[i] = 0.0;  // padded node columns stay zero for the whole kernel
+    for (int i = lane; i < 2 * YW; i += 32) sY[i] = 0.0;
+    unsigned long long halo_epoch = 0;
+    if (p.fused) {   // ghost entries of x: every neighbour's push of this exchange has landed (flags in the local window);
+        // every colour launch checks (the later ones find the flags raised), the last launch's last CTA advances the epoch
+        halo_epoch = *reinterpret_cast<volatile unsigned long long *>(&p.fz.pd.win[p.fz.pd.rank]->halo_epoch) + 1ull;
+        if (tid < p.fz.nneigh) p2p_wait(p.fz.pd, &p.fz.pd.win[p.fz.pd.rank]->hflag[p.fz.neigh[tid]], halo_epoch);
+    }
     __syncthreads();
 
     double dsum[1] = {0.0};
@@ -194,6 +205,15 @@ __global__ void __launch_bounds__(128) k_ebe_mma(EbeArgs p) {
 #pragma unroll
                     for (int d = 0; d < ND; d++)
                         asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d32 + (uint32_t)(d * EW * RSX) * 8u), "l"(src + d) : "memory");
+                    // y of the node, one group ahead as well: the elements of a colour launch share no node, so nobody writes
+                    // these rows before this warp adds to them (the previous colour was another launch: L1 holds nothing stale)
+                    if (!((uint32_t)ent >> 31)) {
+                        const double *ysrc = p.y + (int64_t)((uint32_t)ent & EC_NODE) * ND;
+                        const uint32_t y32 = (uint32_t)__cvta_generic_to_shared(sY + buf * YW + e * RSX + a);
+#pragma unroll
+                        for (int d = 0; d < ND; d++)
+                            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(y32 + (uint32_t)(d * EW * RSX) * 8u), "l"(ysrc + d) : "memory");
+                    }
                 } else {
 #pragma unroll
                     for (int d = 0; d < ND; d++) dst[d * EW * RSX] = 0.0;
@@ -206,6 +226,11 @@ __global__ void __launch_bounds__(128) k_ebe_mma(EbeArgs p) {
     load_conn(g);
     issue_copies(0);
     load_conn(g + stride);
+    auto load_einfo = [&](int64_t gg) -> int {           // record of this lane's element in group gg (0 past the end)
+        const int64_t e = p.e_begin + gg * EW + er;
+        return (gg < ngroups && e < p.e_end) ? p.einfo[e] : 0;
+    };
+    int ei_next = load_einfo(g);
     int buf = 0;
     for (; g < ngroups; g += stride, buf ^= 1) {
         const int64_t e0 = p.e_begin + g * EW;
@@ -214,9 +239,9 @@ __global__ void __launch_bounds__(128) k_ebe_mma(EbeArgs p) {
         // ---- geometry / tangent of this lane's integration points: issued first, consumed after contraction 1
         const int64_t ipl = (e0 + er) * NIP + j * IPL;   // first IP of the lane inside the batch
         double Ji[IPL][ND * ND], coef[IPL], wv[IPL][6];
-        int ei = 0;
+        const int ei = ei_next;                          // loaded one group ago
+        ei_next = load_einfo(g + stride);
         if (act) {
-            ei = p.einfo[e0 + er];
 #pragma unroll
             for (int k = 0; k < ND * ND + 1; k++) {
                 const double *src = p.geo + (int64_t)k * p.nipb + ipl;
@@ -301,6 +326,7 @@ __global__ void __launch_bounds__(128) k_ebe_mma(EbeArgs p) {
         double F[ND][NT3][2];
         int64_t yk[NT3][2];
         uint32_t skip = 0;
+        const double *ya = sY + buf * YW + er * RSX;
 #pragma unroll
         for (int n = 0; n < NT3; n++)
 #pragma unroll
@@ -310,8 +336,10 @@ __global__ void __launch_bounds__(128) k_ebe_mma(EbeArgs p) {
                 const bool st = !(ent >> 31);            // ghost rows belong to the neighbour rank
                 yk[n][c] = st ? (int64_t)(ent & EC_NODE) * ND : -1;
                 if (p.mask) skip |= ((ent >> 28) & 7u) << ((n * 2 + c) * ND);
+                // unconditional read of the staged value (no lane-dependent select in front of mma.sync); rows that are not
+                // stored (ghost, padding, empty slots) may hold anything finite: the stage is zero-initialised
 #pragma unroll
-                for (int i = 0; i < ND; i++) F[i][n][c] = st ? p.y[yk[n][c] + i] : 0.0;
+                for (int i = 0; i < ND; i++) F[i][n][c] = ya[i * EW * RSX + a];
             }
 #pragma unroll
         for (int s = 0; s < KS3; s++) {
@@ -349,6 +377,13 @@ __global__ void __launch_bounds__(128) k_ebe_mma(EbeArgs p) {
                     if (!(acc > 0.0)) p.scal->done = 3;   // not SPD / breakdown
                     p.scal->alpha = p.scal->rz_old / acc;
                 }
+            }
+            if (p.fused && p.last) {   // this rank's p.Ap -> every rank's window (summed in rank order by the vector update)
+                __syncthreads();
+                P2PWin *me = p.fz.pd.win[p.fz.pd.rank];
+                const unsigned long long se = *reinterpret_cast<volatile unsigned long long *>(&me->scal_epoch) + 1ull;
+                if (tid < 32) p2p_push_scalars(p.fz.pd, se, p.scal->acc, 1, tid);
+                if (tid == 0) me->halo_epoch = halo_epoch;
             }
         }
     }

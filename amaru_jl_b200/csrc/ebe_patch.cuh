@@ -43,6 +43,8 @@ struct PatchArgs {
     double *epatch;             // [npatch]
     CgScalars *scal;
     int dot, first, last, finalize, check_done;
+    int fused;                  // multi-GPU fused CG loop (p2p.cuh): wait here for the neighbours' halo of x, push p.Ap to the peers
+    P2PFused fz;
 };
 
 constexpr int EP_PLASTIC = 1 << 29;
@@ -115,6 +117,11 @@ __global__ void __launch_bounds__(128, 2) k_ebe_patch(PatchArgs p) {
     if (smats)
         for (int i = tid; i < 3 * p.nmats; i += NT) sDog[i] = p.dog[i];
     const unsigned int epoch = *reinterpret_cast<volatile unsigned int *>(p.epoch) + 1u;
+    unsigned long long halo_epoch = 0;
+    if (p.fused) {   // ghost entries of x: every neighbour's push of this exchange has landed (flags in the local window)
+        halo_epoch = *reinterpret_cast<volatile unsigned long long *>(&p.fz.pd.win[p.fz.pd.rank]->halo_epoch) + 1ull;
+        if (tid < p.fz.nneigh) p2p_wait(p.fz.pd, &p.fz.pd.win[p.fz.pd.rank]->hflag[p.fz.neigh[tid]], halo_epoch);
+    }
     __syncthreads();
 
     double Ji[IPL][ND * ND], coef[IPL], wv[IPL][6];
@@ -404,6 +411,15 @@ __global__ void __launch_bounds__(128, 2) k_ebe_patch(PatchArgs p) {
                 p.scal->alpha = p.scal->rz_old / acc;
             }
         }
+    }
+    if (p.fused && p.last) {
+        P2PWin *me = p.fz.pd.win[p.fz.pd.rank];
+        if (p.dot) {   // this rank's p.Ap -> every rank's window; the vector-update kernel sums the slots in rank order
+            __syncthreads();
+            const unsigned long long se = *reinterpret_cast<volatile unsigned long long *>(&me->scal_epoch) + 1ull;
+            if (tid < 32) p2p_push_scalars(p.fz.pd, se, p.scal->acc, 1, tid);
+        }
+        if (tid == 0) me->halo_epoch = halo_epoch;
     }
     if (tid == 0) {
         *p.ticket = 0u;

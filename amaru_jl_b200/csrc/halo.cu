@@ -84,6 +84,12 @@ struct HaloComm {
     int64_t *d_send_ptr = nullptr;
     int *d_neigh = nullptr;
     unsigned int *d_counter = nullptr;
+    // fused CG loop (p2p.cuh): per-owned-node table of the ghost slots the node's p entry is pushed into
+    std::vector<int32_t> h_send_nodes;
+    int32_t *d_bidx = nullptr, *d_bent_ptr = nullptr, *d_bent_q = nullptr;
+    int64_t *d_bent_remote = nullptr;
+    unsigned int *d_fcounter = nullptr;
+    bool fused_ready = false;
 };
 
 __global__ void k_pack(int64_t n, int nd, const int32_t *__restrict__ nodes, const double *__restrict__ v, double *buf) {
@@ -144,7 +150,7 @@ __global__ void k_p2p_allreduce(P2PDev pd, double *vals, int n, int op) {
 
 __global__ void k_p2p_halo(P2PDev pd, int nneigh, const int *__restrict__ neigh, const int64_t *__restrict__ send_ptr,
                            const int32_t *__restrict__ send_nodes, double *const *__restrict__ peer_v,
-                           const int64_t *__restrict__ peer_start, int nd, const double *__restrict__ v, unsigned int *counter) {
+                           const int64_t *__restrict__ peer_start, int nd, const double *__restrict__ v, unsigned int *counter, int wait) {
     __shared__ bool last;
     P2PWin *me = pd.win[pd.rank];
     if (*reinterpret_cast<volatile int *>(&me->abort)) return;
@@ -165,10 +171,10 @@ __global__ void k_p2p_halo(P2PDev pd, int nneigh, const int *__restrict__ neigh,
         if (threadIdx.x < nneigh) {
             __threadfence_system();
             st_release_sys(&pd.win[neigh[threadIdx.x]]->hflag[pd.rank], epoch);
-            p2p_wait(pd, &me->hflag[neigh[threadIdx.x]], epoch);
+            if (wait) p2p_wait(pd, &me->hflag[neigh[threadIdx.x]], epoch);
         }
         __syncthreads();
-        if (threadIdx.x == 0) me->halo_epoch = epoch;
+        if (threadIdx.x == 0 && wait) me->halo_epoch = epoch;   // push-only: the consuming kernel advances the epoch
     }
 }
 
@@ -195,6 +201,7 @@ void amaru_comm_setup(amaru_model *m, int nneigh, const int32_t *neigh_rank, con
     hc->recv_start.assign(recv_start, recv_start + nneigh);
     hc->recv_count.assign(recv_count, recv_count + nneigh);
     hc->nsend = send_ptr[nneigh];
+    hc->h_send_nodes.assign(send_nodes, send_nodes + hc->nsend);
     if (const char *e = getenv("AMARU_P2P_TIMEOUT_MS")) hc->timeout_ns = (unsigned long long)std::max(1, atoi(e)) * 1000000ull;
     for (int q = 0; q < nneigh; q++) {
         AMARU_REQUIRE(neigh_rank[q] >= 0 && neigh_rank[q] < m->nranks && neigh_rank[q] != m->rank, AMARU_ERR_ARG, "bad neighbour rank");
@@ -226,6 +233,11 @@ void amaru_comm_destroy(amaru_model *m) {
     cudaFree(hc->d_send_ptr);
     cudaFree(hc->d_neigh);
     cudaFree(hc->d_counter);
+    cudaFree(hc->d_bidx);
+    cudaFree(hc->d_bent_ptr);
+    cudaFree(hc->d_bent_q);
+    cudaFree(hc->d_bent_remote);
+    cudaFree(hc->d_fcounter);
     cudaFree(hc->d_send_nodes);
     cudaFree(hc->d_sendbuf);
     delete hc;
@@ -257,7 +269,7 @@ void amaru_halo_exchange(amaru_model *m, double *d_v) {
         const int64_t n = hc->nsend * m->nd;
         const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, (int64_t)m->nsm * 2));
         k_p2p_halo<<<blocks, 256, 0, m->stream>>>(make_pd(m, hc), hc->nneigh, hc->d_neigh, hc->d_send_ptr, hc->d_send_nodes, peer,
-                                                  hc->d_peer_start, m->nd, d_v, hc->d_counter);
+                                                  hc->d_peer_start, m->nd, d_v, hc->d_counter, 1);
         m->launches++;
         CUDA_CHECK(cudaGetLastError());
         return;
@@ -349,8 +361,80 @@ static void upload_peer_tables(amaru_model *m, HaloComm *hc, const std::vector<d
     if (hc->nneigh) CUDA_CHECK(cudaMemcpy(hc->d_peer_start, peer_recv_start, hc->nneigh * sizeof(int64_t), cudaMemcpyHostToDevice));
     CUDA_CHECK(cudaMemcpy(hc->d_send_ptr, hc->send_ptr.data(), (hc->nneigh + 1) * sizeof(int64_t), cudaMemcpyHostToDevice));
     if (hc->nneigh) CUDA_CHECK(cudaMemcpy(hc->d_neigh, hc->neigh.data(), hc->nneigh * sizeof(int), cudaMemcpyHostToDevice));
+    // boundary table of the fused loop: for every owned node on a send list, the (neighbour, remote node) pairs it goes to
+    {
+        std::vector<int32_t> bidx((size_t)std::max<int64_t>(m->nowned, 1), -1), cnt;
+        std::vector<int32_t> order;                       // boundary nodes in first-seen order
+        for (int q = 0; q < hc->nneigh; q++)
+            for (int64_t k = hc->send_ptr[(size_t)q]; k < hc->send_ptr[(size_t)q + 1]; k++) {
+                const int32_t n = hc->h_send_nodes[(size_t)k];
+                if (bidx[(size_t)n] < 0) {
+                    bidx[(size_t)n] = (int32_t)order.size();
+                    order.push_back(n);
+                    cnt.push_back(0);
+                }
+                cnt[(size_t)bidx[(size_t)n]]++;
+            }
+        std::vector<int32_t> ptr(order.size() + 1, 0);
+        for (size_t i = 0; i < order.size(); i++) ptr[i + 1] = ptr[i] + cnt[i];
+        std::vector<int32_t> bq((size_t)std::max<int64_t>(hc->nsend, 1), 0), fill(ptr.begin(), ptr.end() - 1);
+        std::vector<int64_t> br((size_t)std::max<int64_t>(hc->nsend, 1), 0);
+        for (int q = 0; q < hc->nneigh; q++)
+            for (int64_t k = hc->send_ptr[(size_t)q]; k < hc->send_ptr[(size_t)q + 1]; k++) {
+                const int32_t b = bidx[(size_t)hc->h_send_nodes[(size_t)k]];
+                const int32_t at = fill[(size_t)b]++;
+                bq[(size_t)at] = q;
+                br[(size_t)at] = peer_recv_start[q] + (k - hc->send_ptr[(size_t)q]);
+            }
+        CUDA_CHECK(cudaMalloc(&hc->d_bidx, bidx.size() * sizeof(int32_t)));
+        CUDA_CHECK(cudaMalloc(&hc->d_bent_ptr, ptr.size() * sizeof(int32_t)));
+        CUDA_CHECK(cudaMalloc(&hc->d_bent_q, bq.size() * sizeof(int32_t)));
+        CUDA_CHECK(cudaMalloc(&hc->d_bent_remote, br.size() * sizeof(int64_t)));
+        CUDA_CHECK(cudaMalloc(&hc->d_fcounter, sizeof(unsigned int)));
+        CUDA_CHECK(cudaMemset(hc->d_fcounter, 0, sizeof(unsigned int)));
+        CUDA_CHECK(cudaMemcpy(hc->d_bidx, bidx.data(), bidx.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+        CUDA_CHECK(cudaMemcpy(hc->d_bent_ptr, ptr.data(), ptr.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+        CUDA_CHECK(cudaMemcpy(hc->d_bent_q, bq.data(), bq.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+        CUDA_CHECK(cudaMemcpy(hc->d_bent_remote, br.data(), br.size() * sizeof(int64_t), cudaMemcpyHostToDevice));
+        hc->fused_ready = true;
+    }
     CUDA_CHECK(cudaDeviceSynchronize());
     hc->p2p_ready = true;
+}
+
+// the CG loop may fold its exchanges into the producing / consuming kernels (AMARU_P2P_FUSED=0 keeps the stand-alone kernels)
+bool amaru_comm_fused(const amaru_model *m) {
+    const HaloComm *hc = static_cast<const HaloComm *>(m->comm);
+    if (!hc || !hc->p2p || !hc->fused_ready) return false;
+    const char *e = getenv("AMARU_P2P_FUSED");
+    return !(e && atoi(e) == 0);
+}
+
+P2PFused amaru_comm_fused_args(amaru_model *m) {
+    HaloComm *hc = static_cast<HaloComm *>(m->comm);
+    P2PFused f;
+    f.pd = make_pd(m, hc);
+    f.nneigh = hc->nneigh;
+    f.neigh = hc->d_neigh;
+    f.peer_p = hc->d_peer_p;
+    f.bidx = hc->d_bidx;
+    f.bent_ptr = hc->d_bent_ptr;
+    f.bent_q = hc->d_bent_q;
+    f.bent_remote = hc->d_bent_remote;
+    f.counter = hc->d_fcounter;
+    return f;
+}
+
+// producer half of a halo exchange of p (the consumer is the operator kernel of the fused loop): push + flags, no wait
+void amaru_halo_push(amaru_model *m, double *d_v) {
+    HaloComm *hc = static_cast<HaloComm *>(m->comm);
+    AMARU_REQUIRE(hc && hc->p2p && d_v == m->d_p, AMARU_ERR_COMM, "halo push: peer-memory path of p only");
+    const int64_t n = hc->nsend * m->nd;
+    const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, (int64_t)m->nsm * 2));
+    k_p2p_halo<<<blocks, 256, 0, m->stream>>>(make_pd(m, hc), hc->nneigh, hc->d_neigh, hc->d_send_ptr, hc->d_send_nodes, hc->d_peer_p,
+                                              hc->d_peer_start, m->nd, d_v, hc->d_counter, 0);
+    m->launches++;
+    CUDA_CHECK(cudaGetLastError());
 }
 
 // ---- in-process variant (amaru_create with ngpus > 1): the parts are devices of this process with peer access enabled;

@@ -69,6 +69,9 @@ struct P2PFused {
     unsigned int *counter;          // last-CTA detection of the vector kernels
 };
 
+struct amaru_model;
+P2PFused amaru_comm_fused_args(amaru_model *m);   // halo.cu
+
 // lanes 0..nranks-1 of one warp
 __device__ __forceinline__ void p2p_push_scalars(const P2PDev &pd, unsigned long long epoch, const double *vals, int n, int lane) {
     if (lane < pd.nranks) {

@@ -19,6 +19,7 @@
 #include <cstdlib>
 #include <cstring>
 
+#include "p2p.cuh"
 #include "reduce.cuh"
 
 namespace {
@@ -135,6 +136,124 @@ k_cg_update(int64_t nnodes, const double *__restrict__ p, const double *__restri
                 else if (!(s[1] == s[1])) scal->done = 3;
             }
         }
+    }
+}
+
+
+// ---- fused multi-GPU loop (p2p.cuh): the scalar all-reduces and the halo push live inside the vector kernels ---------------
+// k_cg_update_f: every CTA collects the all-reduced p.Ap (pushed by the operator kernel's last CTA) -> alpha; the last CTA
+// pushes this rank's {r.z, r.r} to every rank and advances scal_epoch.
+template <int BS, bool BLOCKJ>
+__global__ void __launch_bounds__(ROW_THREADS)
+k_cg_update_f(int64_t nnodes, const double *__restrict__ p, const double *__restrict__ q, const double *__restrict__ Minv,
+              double *x, double *r, double *z, double *partial, CgScalars *scal, P2PFused fz) {
+    if (scal->done) return;
+    __shared__ double s_pq;
+    __shared__ int s_ok;
+    P2PWin *me = fz.pd.win[fz.pd.rank];
+    const unsigned long long base = *reinterpret_cast<volatile unsigned long long *>(&me->scal_epoch);
+    if (threadIdx.x == 0) {
+        double v[1] = {0.0};
+        s_ok = p2p_collect(fz.pd, base + 1, v, 1) ? 1 : 0;
+        s_pq = v[0];
+    }
+    __syncthreads();
+    if (!s_ok) return;                                   // a peer left the sequence: the host reports AMARU_ERR_COMM
+    const double pq_all = s_pq;
+    const double alpha = scal->rz_old / pq_all;
+    double s[2] = {0.0, 0.0};
+    for (int64_t n = blockIdx.x * (int64_t)ROW_THREADS + threadIdx.x; n < nnodes; n += (int64_t)gridDim.x * ROW_THREADS) {
+        double rr[BS], zz[BS];
+#pragma unroll
+        for (int i = 0; i < BS; i++) {
+            const int64_t k = n * BS + i;
+            x[k] += alpha * p[k];
+            rr[i] = r[k] - alpha * q[k];
+            r[k] = rr[i];
+        }
+        apply_minv<BS, BLOCKJ>(Minv, n, rr, zz);
+#pragma unroll
+        for (int i = 0; i < BS; i++) {
+            z[n * BS + i] = zz[i];
+            s[0] += rr[i] * zz[i];
+            s[1] += rr[i] * rr[i];
+        }
+    }
+    block_sum<2, ROW_THREADS>(s);
+    if (publish_partials<2>(s, partial, &scal->counter[1])) {
+        sum_partials<2, ROW_THREADS>(s, partial);
+        __shared__ double s_out[2];
+        if (threadIdx.x == 0) {
+            s_out[0] = s[0];
+            s_out[1] = s[1];
+            scal->pq = pq_all;                           // for the breakdown test of the p-update
+        }
+        __syncthreads();
+        if (threadIdx.x < 32) p2p_push_scalars(fz.pd, base + 2, s_out, 2, threadIdx.x);
+        if (threadIdx.x == 0) me->scal_epoch = base + 1;
+    }
+}
+
+// k_cg_pupdate_f: every CTA collects the all-reduced {r.z, r.r} -> beta and the convergence decision (identical everywhere);
+// p = z + beta p with the entries of boundary nodes stored straight into the neighbours' ghost slots; the last CTA raises
+// the halo flags (the next operator kernel waits for them), does the scalar bookkeeping and advances scal_epoch.
+template <int BS>
+__global__ void __launch_bounds__(ROW_THREADS)
+k_cg_pupdate_f(int64_t nnodes, const double *__restrict__ z, double *p, CgScalars *scal, P2PFused fz) {
+    if (scal->done) return;
+    __shared__ double s_v[2];
+    __shared__ int s_ok, s_last;
+    P2PWin *me = fz.pd.win[fz.pd.rank];
+    const unsigned long long base = *reinterpret_cast<volatile unsigned long long *>(&me->scal_epoch);
+    const unsigned long long he = *reinterpret_cast<volatile unsigned long long *>(&me->halo_epoch) + 1ull;
+    if (threadIdx.x == 0) {
+        double v[2] = {0.0, 0.0};
+        s_ok = p2p_collect(fz.pd, base + 1, v, 2) ? 1 : 0;
+        s_v[0] = v[0];
+        s_v[1] = v[1];
+    }
+    __syncthreads();
+    if (!s_ok) return;
+    const double rz_new = s_v[0], rr = s_v[1];
+    const double beta = rz_new / scal->rz_old;
+    int done = 0;
+    if (!(scal->pq > 0.0)) done = 3;                     // not SPD / breakdown
+    else if (rr <= scal->tol2 * scal->bb) done = 1;
+    else if (scal->iters + 1 >= scal->maxit) done = 2;
+    else if (!(rr == rr)) done = 3;
+    if (!done) {
+        for (int64_t n = blockIdx.x * (int64_t)ROW_THREADS + threadIdx.x; n < nnodes; n += (int64_t)gridDim.x * ROW_THREADS) {
+            double pn[BS];
+#pragma unroll
+            for (int i = 0; i < BS; i++) {
+                pn[i] = z[n * BS + i] + beta * p[n * BS + i];
+                p[n * BS + i] = pn[i];
+            }
+            const int32_t b = fz.bidx[n];
+            if (b >= 0)
+                for (int32_t e = fz.bent_ptr[b]; e < fz.bent_ptr[b + 1]; e++) {
+                    double *dst = fz.peer_p[fz.bent_q[e]] + fz.bent_remote[e] * BS;
+#pragma unroll
+                    for (int i = 0; i < BS; i++) dst[i] = pn[i];
+                }
+        }
+        __threadfence_system();
+    }
+    __syncthreads();                                     // every thread read the scalars and fenced its remote stores
+    if (threadIdx.x == 0) s_last = atomicInc(fz.counter, gridDim.x - 1) == gridDim.x - 1;
+    __syncthreads();
+    if (!s_last) return;
+    if (!done && threadIdx.x < fz.nneigh) {
+        __threadfence_system();
+        st_release_sys(&fz.pd.win[fz.neigh[threadIdx.x]]->hflag[fz.pd.rank], he);
+    }
+    if (threadIdx.x == 0) {
+        scal->beta = beta;
+        scal->rz_old = rz_new;
+        scal->rr = rr;
+        scal->iters += 1;
+        scal->done = done;
+        me->scal_epoch = base + 1;
     }
 }
 
@@ -295,7 +414,7 @@ static void amaru_system_product(amaru_model *m, const double *x, double *y) {
     else amaru_spmv(m, m->d_A, x, y, 0);
 }
 
-static void spmv_dot(amaru_model *m, const double *A, const double *x, double *y, int finalize) {
+static void spmv_dot(amaru_model *m, const double *A, const double *x, double *y, int finalize, int fused = 0) {
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (m->profiling) {   // the pool owns the events from the moment they exist (released with the profile / the handle)
         CUDA_CHECK(cudaEventCreate(&e0));
@@ -304,7 +423,7 @@ static void spmv_dot(amaru_model *m, const double *A, const double *x, double *y
         m->ev_pool.push_back(e1);
         CUDA_CHECK(cudaEventRecord(e0, m->stream));
     }
-    if (m->op_ebe && !m->blended && A == m->d_A) amaru_ebe_apply(m, x, y, 1, 1, 1, finalize);               // matrix-free (ebe.cu)
+    if (m->op_ebe && !m->blended && A == m->d_A) amaru_ebe_apply(m, x, y, 1, 1, 1, finalize, fused);        // matrix-free (ebe.cu)
     else if (m->use_sym && A == m->d_A) amaru_spmv_sym_launch(m, x, y, 1, 1, 1, finalize);   // half the bytes (spmv.cu)
     else amaru_spmv_launch(m, A, x, y, 1, 1, 1, finalize);
     if (m->profiling) CUDA_CHECK(cudaEventRecord(e1, m->stream));
@@ -373,11 +492,22 @@ static void cg_loop(amaru_model *m, double rtol, int maxit, SolveInfo &info) {
     // peer-memory exchanges are plain kernels with device-resident epochs, so partitioned handles replay graphs too; with
     // NCCL calls between the kernels (the default between processes until amaru_p2p_enable) the batch is launched directly
     const bool p2p = multi && amaru_comm_is_p2p(m);
+    // fused loop: operator + 2 vector kernels per iteration, no stand-alone exchange kernels (DMMA forms of the matrix-free operator)
+    const bool fused = p2p && amaru_comm_fused(m) && m->op_ebe && !m->blended && amaru_ebe_fusable(m);
+    if (fused) amaru_halo_push(m, m->d_p);               // p of the first iteration; consumed by the first operator kernel
     const bool use_graph = !m->profiling && m->cg_graph && (!multi || p2p);
     bool finished = false;
     int64_t batch_launches = 0;
     auto one_batch = [&]() {
-        for (int it = 0; it < CG_BATCH; it++) {
+        for (int it = 0; it < CG_BATCH && fused; it++) {
+            spmv_dot(m, m->d_A, m->d_p, m->d_q, 0, 1);
+            const P2PFused fz = amaru_comm_fused_args(m);
+            k_cg_update_f<BS, BJ><<<gn, ROW_THREADS, 0, m->stream>>>(m->nowned, m->d_p, m->d_q, m->d_Minv, m->d_x, m->d_r, m->d_z,
+                                                                      m->d_partial, m->d_scal, fz);
+            k_cg_pupdate_f<BS><<<gn, ROW_THREADS, 0, m->stream>>>(m->nowned, m->d_z, m->d_p, m->d_scal, fz);
+            m->launches += 2;
+        }
+        for (int it = 0; it < CG_BATCH && !fused; it++) {
             if (multi) amaru_halo_exchange(m, m->d_p);
             spmv_dot(m, m->d_A, m->d_p, m->d_q, fin);
             // multi-GPU: per iteration = halo exchange, operator, all-reduce(p.Ap), update, all-reduce(r.z, r.r), one scalar

@@ -918,19 +918,23 @@ void launch_stream(amaru_model *m, const double *A, const double *x, double *y, 
             m->tile_xcap, m->spmv_stages, m->spmv_xd, m->spmv_sleep, m->d_partial, m->d_scal, check_done, finalize);
 }
 
+// The attribute is per function and device, and the dynamic size depends on the model's tile geometry: handles of different
+// sizes live on one device (a group part next to a single-GPU handle), so the cap is the same constant for all of them.
+constexpr int SPMV_SMEM_CAP = 220 * 1024;
+
 template <int BS>
 bool configure_stream(amaru_model *m) {
     const StageLayout L = stage_layout(BS, m->tile_blks, m->tile_rows, m->tile_xcap);
     const size_t smem = m->spmv_stages * L.vbytes + (size_t)(m->spmv_stages + m->spmv_xd) * (L.rbytes + L.xbytes);
-    if (smem > 220 * 1024) return false;
+    if (smem > (size_t)SPMV_SMEM_CAP) return false;
     int occ = 0;
     if (m->spmv_ver == 2) {
-        CUDA_CHECK(cudaFuncSetAttribute(k_spmv_stream2<BS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CUDA_CHECK(cudaFuncSetAttribute(k_spmv_stream2<BS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_CHECK(cudaFuncSetAttribute(k_spmv_stream2<BS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SPMV_SMEM_CAP));
+        CUDA_CHECK(cudaFuncSetAttribute(k_spmv_stream2<BS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SPMV_SMEM_CAP));
         CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_spmv_stream2<BS, true>, STREAM2_THREADS, smem));
     } else {
-        CUDA_CHECK(cudaFuncSetAttribute(k_spmv_stream<BS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CUDA_CHECK(cudaFuncSetAttribute(k_spmv_stream<BS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_CHECK(cudaFuncSetAttribute(k_spmv_stream<BS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SPMV_SMEM_CAP));
+        CUDA_CHECK(cudaFuncSetAttribute(k_spmv_stream<BS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SPMV_SMEM_CAP));
         CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_spmv_stream<BS, true>, STREAM_THREADS, smem));
     }
     if (occ < 1) return false;
@@ -951,10 +955,10 @@ bool configure_sym(amaru_model *m) {
     const StageLayout L = stage_layout(BS, m->tile_blks, m->tile_rows, m->stile_xcap);
     const size_t smem = m->spmv_stages * L.vbytes + (size_t)(m->spmv_stages + m->spmv_xd) * (L.rbytes + L.xbytes) +
                         (size_t)m->sym_ystages * NCW * L.xbytes;
-    if (smem > 220 * 1024) return false;
+    if (smem > (size_t)SPMV_SMEM_CAP) return false;
     int occ = 0;
-    CUDA_CHECK(cudaFuncSetAttribute(k_spmv_sym<BS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CUDA_CHECK(cudaFuncSetAttribute(k_spmv_sym<BS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_CHECK(cudaFuncSetAttribute(k_spmv_sym<BS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SPMV_SMEM_CAP));
+    CUDA_CHECK(cudaFuncSetAttribute(k_spmv_sym<BS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SPMV_SMEM_CAP));
     CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_spmv_sym<BS, true>, SYM_THREADS, smem));
     if (occ < 1) return false;
     m->sgrid = std::min(m->nsm * occ, m->nstiles);

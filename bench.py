@@ -361,7 +361,9 @@ def main():
         ach = 2.0 * fma / (avg_spmv_ms * 1e-3) / 1e12
         fp64 = {"achieved_tflops": ach, "peak_tflops": fpk, "frac": ach / fpk if fpk else None,
                 "peak_source": "profiles/fp64_peak_r2.json (DFMA microbenchmark on this pool's B200, sustained)"}
-    kdesc = ("matrix-free element-by-element tangent operator + fused p.Ap, one launch per element colour; per application"
+    kdesc = (("matrix-free tangent operator on the FP64 tensor cores (DMMA) + fused p.Ap, x / y of a 64-element patch in shared "
+              "memory, one launch per application" if "patch" in dm.spmv_kernel else
+              "matrix-free tangent operator (DMMA) + fused p.Ap, one launch per element colour; per application")
              if is_ebe else "TMA-streamed, warp-specialised block-CSR SpMV + p.Ap dot")
     cg_iters = [p["cg_iters"] for p in phases]
     # whole-iteration algorithmic bytes of this rank

@@ -5,6 +5,7 @@ import sys
 
 faulthandler.dump_traceback_later(25, exit=True)
 os.environ.setdefault("AMARU_EBE_PATCH_MINFILL", "0")
+os.environ.setdefault("AMARU_EBE_PATCH_MINPATCH", "0")
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
 import numpy as np

@@ -32,6 +32,7 @@ ap.add_argument("--scale", type=float, default=1.0)
 ap.add_argument("--nincs", type=int, default=0)
 ap.add_argument("--autoinc", action="store_true")
 ap.add_argument("--cg-rtol", type=float, default=1e-10)
+ap.add_argument("--uz", type=float, default=-0.01, help="config 3: prescribed footing displacement")
 ap.add_argument("--out", default="gpurun_out/full_configs_r2.jsonl")
 args = ap.parse_args()
 
@@ -58,10 +59,10 @@ elif args.config == 3:
     mesh = Mesh(Block([[0, 0, 0], [1, 1, 1]], nx=n, ny=n, nz=n, cellshape="HEX20", tag="solids"))
     model = FEModel(mesh, [("solids", MechSolid, VonMises, dict(E=210e6, nu=0.3, fy=240e3, H=0.0))], MechContext())
     bcs = [("z==0", NodeBC(ux=0, uy=0, uz=0)),
-           ("z==1 and x>=0.4 and x<=0.6 and y>=0.4 and y<=0.6", NodeBC(uz=-0.01))]
+           ("z==1 and x>=0.4 and x<=0.6 and y>=0.4 and y<=0.6", NodeBC(uz=args.uz))]
     ana = MechAnalysis(model)
     addstage(ana, bcs, nincs=args.nincs or 10)
-    name = "configs[2]: HEX20 von Mises footing, 10 Newton-Raphson load increments"
+    name = f"configs[2]: HEX20 von Mises footing (uz = {args.uz}), 10 Newton-Raphson load increments" + (" (autoinc)" if args.autoinc else "")
     t0 = time.perf_counter()
     status = solve(ana, autoinc=args.autoinc, **kw)
     base = np.abs(model.coords[:, 2]) < 1e-9

@@ -49,6 +49,9 @@ def main():
             return out
         assert dm.p2p_connect(gather), "peer-memory path could not be enabled"
     ok = True
+    if rank == 0:
+        print(f"operator kernel: {dm.spmv_kernel}; AMARU_P2P={os.environ.get('AMARU_P2P', '0')} "
+              f"AMARU_P2P_FUSED={os.environ.get('AMARU_P2P_FUSED', '1')}", flush=True)
     ref = L.DeviceModel(flat, eqid, ndofs, nu, device=local) if rank == 0 else None
     for it in range(2):                                    # second pass: tangent on the plastic trial state
         dm.assemble_K()

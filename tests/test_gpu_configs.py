@@ -76,8 +76,8 @@ def test_config3_footing_reduced_vs_oracle():
     r, Uacc, om = oracle_run(ref, [(bcs, 10)], maxits=5)
     assert status.success == r["success"]
     assert len(ana.stats) == r["its"]
-    assert rel(model.U, Uacc) < 1e-7
-    assert rel(model.state["sigma"], om.sig) < 1e-6
+    assert rel(model.U, Uacc) < 1e-8
+    assert rel(model.state["sigma"], om.sig) < 1e-7
     assert (om.epa > 0).sum() > 0 and np.array_equal(model.state["epa"] > 0, om.epa > 0)
 
 
@@ -95,8 +95,8 @@ def test_config4_tet10_dp_slope_reduced_vs_oracle():
     r, Uacc, om = oracle_run(ref, [(bcs, 4)], tol=1e-3)
     assert status.success == r["success"]
     assert len(ana.stats) == r["its"]
-    assert rel(model.U, Uacc) < 1e-7
-    assert rel(model.state["sigma"], om.sig) < 1e-6
+    assert rel(model.U, Uacc) < 1e-8
+    assert rel(model.state["sigma"], om.sig) < 1e-7
 
 
 def test_config4_tet10_5M_full_size():

@@ -20,6 +20,7 @@ def operator_form(request, monkeypatch):
     even where the small test meshes fill the patch slots poorly) and the colour-ordered k_ebe_mma."""
     if request.param == "patch":
         monkeypatch.setenv("AMARU_EBE_PATCH_MINFILL", "0")
+        monkeypatch.setenv("AMARU_EBE_PATCH_MINPATCH", "0")
     else:
         monkeypatch.setenv("AMARU_EBE_PATCH", "0")
     return request.param
