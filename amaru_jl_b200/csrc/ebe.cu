@@ -12,15 +12,20 @@
 // mech-solid.jl:82-121), σ = coef·a·D·ε, and the nodal force is f_a = Σ_q ∂N_a/∂R(q) · S(q) with S = J⁻¹·T(σ): the shape
 // table is shared by all elements, so both contractions are small GEMMs against a constant operand held in shared memory.
 //
-// One CTA works on groups of NT/NIP elements of ONE colour (elements of a colour share no node: plain read-modify-write of
-// y, fixed order, no atomics — same determinism argument as assemble.cu):
-//   phase 1  gather x of the group's nodes                       (thread = element-node)
-//   phase 2  G, H, ε, σ, S and the energy coef·εᵀDε              (thread = element × integration point)
-//   phase 3  f_a = Σ_q,k dN[q][k][a]·S[q][k][:], y[node] += f_a   (thread = element × TA nodes, register tile TA×nd)
+// Both contractions run on the FP64 tensor cores (DMMA, ebe_mma.cuh: one warp = 8 elements, accumulator registers = the
+// lane's own integration points).  Two forms, chosen per batch at amaru_create:
+//   k_ebe_patch (ebe_patch.cuh)  x / y of a 64-element patch in shared memory, ticketed colour-major patch order with epoch
+//                                flags; for batches with enough patches to hide the 8-deep chain of neighbouring patches;
+//   k_ebe_mma   (ebe_mma.cuh)    element groups straight from global memory, ONE persistent cooperative launch that walks
+//                                through the element colours with a grid barrier between two colours (elements of a colour
+//                                share no node: plain read-modify-write of y, fixed order, no atomics — same determinism
+//                                argument as assemble.cu); for small batches (multi-GPU strong scaling) and poor patch fills.
+// The earlier DFMA form (one thread per integration point, shape table in shared memory) was retired after the A/B of
+// it was bound by the shared-memory pipe (0.97 ms per application at 1 M HEX20 against 0.605 ms).
 // p·Ap = Σ_e Σ_q coef·εᵀDε over the elements this rank owns (p vanishes on prescribed dofs, so this is the masked dot);
-// partial sums are combined in a fixed order by the last block of every colour launch.
+// partial sums are combined in a fixed order by the last CTA of a launch.
 //
-// Algorithmic bytes per application: 8·(nd²+1)·nip + 48·nip(plastic elements) + 4·nn·nelem + 8n + 8n.
+// Algorithmic bytes per application: 8·(nd²+1)·nip + 48·nip(plastic elements) + (2|4)·nn·nelem + 8n + 8n.
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
@@ -31,20 +36,18 @@
 
 namespace {
 
-constexpr int EBE_NT = 128;   // threads per CTA: 16 HEX20 / 32 TET10 elements per group
-
-
 constexpr uint32_t EC_NODE = 0x0fffffffu;   // econn entry: node | prescribed-dof mask << 28 | ghost << 31
 constexpr int EI_PLASTIC = 1 << 30;          // einfo entry: material | plastic << 30 | not-owned << 31
 constexpr int EI_MAT = (1 << 30) - 1;
+constexpr int EBE_MAXCOL = 96;               // element colours one persistent launch walks through (more: several launches)
 constexpr int EBE_SMATS = 32;                // material moduli staged in shared memory up to this many materials
 
 struct EbeBatch {          // per element batch, colour-sorted element order (same order as the IP state planes)
     double *d_geo = nullptr;      // [(nd*nd+1)][nipb]: J⁻¹ row-major planes, then coef
     int32_t *d_econn = nullptr;   // [nelem*nn] node | prescribed-dof mask << 28 | ghost << 31
     int32_t *d_einfo = nullptr;   // [nelem] material | (some IP has w != 0) << 30 | (element owned by another rank) << 31
-    int grid = 1;                 // persistent grid of the DFMA kernel (k_ebe_apply)
-    int grid_mma = 1;             // persistent grid of the DMMA kernel (k_ebe_mma)
+    int grid_mma = 1;             // persistent (co-resident) grid of the colour-ordered DMMA kernel (k_ebe_mma)
+    unsigned int *d_bar = nullptr;   // its grid barrier: arrivals, completed generation
     // patch form (k_ebe_patch, ebe_patch.cuh): arrays in SLOT order (8 element slots per group, groups patch by patch)
     bool patch = false;
     int npatch = 0, grid_patch = 1;
@@ -67,7 +70,7 @@ struct Ebe {
     double *d_dog = nullptr;      // [nmats][3]: c(1-ν), cν, c(1-2ν)
     int64_t *d_nplastic = nullptr;   // device counter of IPs in flagged elements (for the byte count)
     int64_t nplastic_ip = 0;
-    bool mma = true;              // contractions on the FP64 tensor cores (AMARU_EBE_MMA=0: the DFMA kernel, kept for A/B)
+    bool mma = true;              // contractions on the FP64 tensor cores (the DFMA form was retired after the A/B)
     bool want_patch = true;       // patch form where the plan fills its element slots well enough (AMARU_EBE_PATCH=0: never)
     bool memset_y = false;        // some owned node belongs to no element: y is cleared before the patch launches
     unsigned int epoch_base = 0;  // every solve starts a fresh range of application epochs (amaru_ebe_begin)
@@ -89,304 +92,15 @@ struct EbeArgs {
     const double *x;
     double *y;
     int mask;
-    int64_t e_begin, e_end;
+    int ncol;               // non-empty element colours of the batch
+    int64_t cb[EBE_MAXCOL + 1];   // their element ranges [cb[c], cb[c+1]) are consecutive
+    unsigned int *bar;      // grid barrier between two colours
     double *partial;
     CgScalars *scal;
     int dot, first, last, finalize, check_done;
     int fused;              // multi-GPU fused CG loop (p2p.cuh): first launch waits for the halo of x, last launch pushes p.Ap
     P2PFused fz;
 };
-
-template <int NN, int ND, int NIP, int TA, bool MASS, int NT>
-struct EbeLayout {
-    static constexpr int EPB = NT / NIP;                     // elements per group
-    static constexpr int NP = ND * ND + 1;                   // geometry planes
-    static constexpr int QS = (ND * NN) | 1;                 // stride of one integration point in the dN table (odd)
-    static constexpr int US = (NN * ND) | 1;                 // stride of one element in the x stage (odd)
-    static constexpr int SQ = ND * ND + (MASS ? ND : 0);     // S (+ mass vector) of one integration point
-    static constexpr int ES = (NIP * SQ) | 1;                // stride of one element in the S stage (odd)
-    static constexpr int NTH3 = NN / TA;                     // phase-3 node groups per element (x 2 halves of the IPs)
-    static constexpr int NLD = (EPB * NN + NT - 1) / NT;     // element-node ids per thread and group
-    static constexpr int NGC = (NP * (NT / 2) + NT - 1) / NT;   // 16-byte geometry chunks per thread and group
-    static constexpr size_t doubles = (size_t)NIP * QS + (MASS ? NIP * NN : 0) + 3 * EBE_SMATS + (size_t)2 * EPB * US +
-                                      (size_t)2 * NP * NT + (size_t)EPB * ES;
-    static constexpr size_t bytes = doubles * 8 + (size_t)2 * EPB * NN * 4;
-    static_assert(NN % TA == 0, "TA must divide NN");
-    static_assert(EPB * NTH3 * 2 == NT, "phase 3 must use every thread: (NN/TA)*2 == NIP");
-    static_assert(NIP % 2 == 0, "phase 3 splits the integration points in two halves");
-};
-
-// Group pipeline of one CTA (2 barriers per group, nothing but shared memory and registers on the critical path):
-//   (B) x and the geometry planes of group g have landed in stage `buf` (cp.async issued one group earlier) and everybody
-//       left phase 3 of g-1 -> start the cp.async copies of group g+1 into the other stage; the node ids of group g+2 and
-//       the element record of group g+1 go to registers
-//   phase 2 (g): thread = (element, integration point)           -> S stage
-//   (C)
-//   phase 3 (g): thread = (element, TA nodes, half of the IPs); the y entries are loaded into the accumulators up front,
-//       the two halves are combined with one xor-shuffle and each lane stores its share of the TA nodes.
-template <int NN, int ND, int NIP, int TA, bool MASS, int NT>
-__global__ void __launch_bounds__(NT) k_ebe_apply(EbeArgs p) {
-    if (p.check_done && p.scal->done) return;
-    using L = EbeLayout<NN, ND, NIP, TA, MASS, NT>;
-    constexpr int EPB = L::EPB, NP = L::NP, QS = L::QS, US = L::US, SQ = L::SQ, ES = L::ES, NTH3 = L::NTH3, NLD = L::NLD,
-                  NGC = L::NGC;
-    extern __shared__ __align__(16) double esm[];
-    double *sdN = esm;                                   // [NIP][QS]: dN[q][k][a] at q*QS + k*NN + a
-    double *sNf = sdN + NIP * QS;                        // [NIP][NN] (mass only)
-    double *sDog = sNf + (MASS ? NIP * NN : 0);          // [EBE_SMATS][3]
-    double *sU = sDog + 3 * EBE_SMATS;                   // [2][EPB][US]: x of element-node (a, i) at e*US + a*ND + i
-    double *sGeo = sU + 2 * EPB * US;                    // [2][NP][NT]: plane k of IP t at k*NT + t
-    double *sS = sGeo + 2 * NP * NT;                     // [EPB][ES]: S[q][k][i] at e*ES + q*SQ + k*ND + i
-    int32_t *sNode = reinterpret_cast<int32_t *>(sS + EPB * ES);   // [2][EPB][NN] (econn entries)
-    const int tid = threadIdx.x;
-    for (int i = tid; i < NIP * NN * ND; i += NT) {      // global table is [q][a][k]
-        const int q = i / (NN * ND), r = i - q * NN * ND, a = r / ND, k = r - a * ND;
-        sdN[q * QS + k * NN + a] = p.dNdR[i];
-    }
-    if (MASS)
-        for (int i = tid; i < NIP * NN; i += NT) sNf[i] = p.Nf[i];
-    const bool smats = p.nmats <= EBE_SMATS;
-    if (smats)
-        for (int i = tid; i < 3 * p.nmats; i += NT) sDog[i] = p.dog[i];
-    double dsum[1] = {0.0};
-    const int64_t ngroups = (p.e_end - p.e_begin + EPB - 1) / EPB;
-    const int64_t stride = gridDim.x;
-    int32_t nreg[NLD];
-    auto load_conn = [&](int64_t g) {                    // econn entries of group g -> registers (0 nodes past the end)
-        const int64_t ge = p.e_begin + g * EPB;          // first element of the group
-#pragma unroll
-        for (int j = 0; j < NLD; j++) {
-            const int i = tid + j * NT;
-            nreg[j] = (g < ngroups && i < EPB * NN && ge * NN + i < p.e_end * NN) ? p.econn[ge * NN + i] : -1;
-        }
-    };
-    auto load_einfo = [&](int64_t g) -> int {            // record of the element this thread integrates in phase 2
-        const int64_t e = p.e_begin + g * EPB + tid / NIP;
-        return (g < ngroups && e < p.e_end) ? p.einfo[e] : 0;
-    };
-    auto issue_copies = [&](int64_t g, int buf) {        // x of the nodes in nreg and the geometry planes of group g -> stage buf
-#pragma unroll
-        for (int j = 0; j < NLD; j++) {
-            const int i = tid + j * NT;
-            const int32_t ent = nreg[j];
-            if (ent != -1) {
-                sNode[buf * EPB * NN + i] = ent;
-                const int e = i / NN, a = i - e * NN;
-                const uint32_t dst = (uint32_t)__cvta_generic_to_shared(sU + (buf * EPB + e) * US + a * ND);
-                const double *src = p.x + (int64_t)((uint32_t)ent & EC_NODE) * ND;
-#pragma unroll
-                for (int d = 0; d < ND; d++)
-                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + d * 8u), "l"(src + d) : "memory");
-            }
-        }
-        if (g < ngroups) {
-            const int64_t e0 = p.e_begin + g * EPB;
-            const int nv = (int)min((int64_t)EPB, p.e_end - e0) * NIP;   // valid doubles per plane (even)
-            const double *gsrc = p.geo + e0 * NIP;
-            const uint32_t gdst = (uint32_t)__cvta_generic_to_shared(sGeo + buf * NP * NT);
-#pragma unroll
-            for (int j = 0; j < NGC; j++) {
-                const int c = tid + j * NT;
-                const int k = c / (NT / 2), o = (c - k * (NT / 2)) * 2;
-                if (k < NP && o < nv)
-                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(gdst + (uint32_t)(k * NT + o) * 8u),
-                                 "l"(gsrc + (int64_t)k * p.nipb + o) : "memory");
-            }
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-    };
-    load_conn(blockIdx.x);
-    int ei = load_einfo(blockIdx.x);
-    issue_copies(blockIdx.x, 0);
-    load_conn(blockIdx.x + stride);
-    int buf = 0;
-    for (int64_t g = blockIdx.x; g < ngroups; g += stride, buf ^= 1) {
-        const int64_t e0 = p.e_begin + g * EPB;
-        const int ne = (int)min((int64_t)EPB, p.e_end - e0);
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-        __syncthreads();                                 // (B)
-        issue_copies(g + stride, buf ^ 1);
-        load_conn(g + 2 * stride);
-        const int ei_next = load_einfo(g + stride);
-        // ---- phase 2: one thread per (element, integration point)
-        {
-            const int e = tid / NIP, q = tid - e * NIP;
-            if (e < ne) {
-                const double *gp = sGeo + buf * NP * NT + tid;
-                const bool plastic = (ei & EI_PLASTIC) != 0;
-                double w[6];
-                if (plastic) {
-                    const int64_t ip = p.ip_off + (e0 + e) * NIP + q;
-#pragma unroll
-                    for (int c = 0; c < 6; c++) w[c] = p.w[(int64_t)c * p.nip_total + ip];
-                }
-                const double *dg = (smats ? sDog : p.dog) + 3 * (ei & EI_MAT);
-                double G[ND * ND];
-#pragma unroll
-                for (int k = 0; k < ND * ND; k++) G[k] = 0.0;
-                double ub[ND];
-#pragma unroll
-                for (int d = 0; d < ND; d++) ub[d] = 0.0;
-                const double *U = sU + (buf * EPB + e) * US, *dn = sdN + q * QS;
-#pragma unroll 4
-                for (int a = 0; a < NN; a++) {
-                    double u[ND], d_[ND];
-#pragma unroll
-                    for (int i = 0; i < ND; i++) u[i] = U[a * ND + i];
-#pragma unroll
-                    for (int k = 0; k < ND; k++) d_[k] = dn[k * NN + a];
-#pragma unroll
-                    for (int i = 0; i < ND; i++)
-#pragma unroll
-                        for (int k = 0; k < ND; k++) G[i * ND + k] += u[i] * d_[k];
-                    if (MASS) {
-                        const double n = sNf[q * NN + a];
-#pragma unroll
-                        for (int i = 0; i < ND; i++) ub[i] += n * u[i];
-                    }
-                }
-                double Ji[ND * ND];
-#pragma unroll
-                for (int k = 0; k < ND * ND; k++) Ji[k] = gp[k * NT];
-                const double coef = gp[ND * ND * NT];
-                double H[ND * ND];
-#pragma unroll
-                for (int i = 0; i < ND; i++)
-#pragma unroll
-                    for (int j = 0; j < ND; j++) {
-                        double v = 0.0;
-#pragma unroll
-                        for (int k = 0; k < ND; k++) v += G[i * ND + k] * Ji[k * ND + j];
-                        H[i * ND + j] = v;
-                    }
-                double ep[6], sg[6];
-                if constexpr (ND == 3) {
-                    ep[0] = H[0]; ep[1] = H[4]; ep[2] = H[8];
-                    ep[3] = (H[5] + H[7]) / AM_SR2; ep[4] = (H[2] + H[6]) / AM_SR2; ep[5] = (H[1] + H[3]) / AM_SR2;
-                } else {
-                    ep[0] = H[0]; ep[1] = H[3]; ep[2] = 0.0; ep[3] = 0.0; ep[4] = 0.0; ep[5] = (H[1] + H[2]) / AM_SR2;
-                }
-                const double dd = dg[0], oo = dg[1], gg = dg[2];
-                sg[0] = dd * ep[0] + oo * ep[1] + oo * ep[2];
-                sg[1] = oo * ep[0] + dd * ep[1] + oo * ep[2];
-                sg[2] = oo * ep[0] + oo * ep[1] + dd * ep[2];
-                sg[3] = gg * ep[3]; sg[4] = gg * ep[4]; sg[5] = gg * ep[5];
-                if (plastic) {
-                    double t = 0.0;
-#pragma unroll
-                    for (int c = 0; c < 6; c++) t += w[c] * ep[c];
-#pragma unroll
-                    for (int c = 0; c < 6; c++) sg[c] -= w[c] * t;
-                }
-                const double ca = coef * p.sa;
-                double en = 0.0;
-#pragma unroll
-                for (int c = 0; c < 6; c++) {
-                    sg[c] *= ca;
-                    en += ep[c] * sg[c];
-                }
-                double *S = sS + e * ES + q * SQ;
-                if constexpr (ND == 3) {
-                    const double T[9] = {sg[0], sg[5] / AM_SR2, sg[4] / AM_SR2, sg[5] / AM_SR2, sg[1], sg[3] / AM_SR2,
-                                         sg[4] / AM_SR2, sg[3] / AM_SR2, sg[2]};
-#pragma unroll
-                    for (int k = 0; k < 3; k++)
-#pragma unroll
-                        for (int i = 0; i < 3; i++) S[k * 3 + i] = Ji[k * 3] * T[i * 3] + Ji[k * 3 + 1] * T[i * 3 + 1] + Ji[k * 3 + 2] * T[i * 3 + 2];
-                } else {
-                    const double T[4] = {sg[0], sg[5] / AM_SR2, sg[5] / AM_SR2, sg[1]};
-#pragma unroll
-                    for (int k = 0; k < 2; k++)
-#pragma unroll
-                        for (int i = 0; i < 2; i++) S[k * 2 + i] = Ji[k * 2] * T[i * 2] + Ji[k * 2 + 1] * T[i * 2 + 1];
-                }
-                if (MASS) {
-                    const double cm = coef * p.sb * p.rho[e0 + e];
-#pragma unroll
-                    for (int i = 0; i < ND; i++) {
-                        S[ND * ND + i] = cm * ub[i];
-                        en += cm * ub[i] * ub[i];
-                    }
-                }
-                if (p.dot && ei >= 0) dsum[0] += en;     // bit 31 of the record: the element belongs to another rank
-            }
-        }
-        ei = ei_next;
-        __syncthreads();                                 // (C)
-        // ---- phase 3: thread = (element, TA nodes, half h of the integration points)
-        {
-            constexpr int TS = (TA + 1) / 2;             // lane h = 0 stores nodes [0, TS), lane h = 1 nodes [TS, TA)
-            const int e = tid / (2 * NTH3), r3 = tid - e * (2 * NTH3), a0 = (r3 >> 1) * TA, h = r3 & 1;
-            const bool active = e < ne;
-            double f[TA][ND];
-            int64_t yk[TA];                              // first dof of the node this lane stores, or -1
-            uint32_t skip = 0;                           // bit t*ND+i: prescribed dof (masked product)
-#pragma unroll
-            for (int t = 0; t < TA; t++) {
-                const bool mine = active && ((t < TS) == (h == 0));
-                const uint32_t ent = mine ? (uint32_t)sNode[(buf * EPB + e) * NN + a0 + t] : 0x80000000u;
-                const bool st = !(ent >> 31);            // ghost rows belong to the neighbour rank
-                yk[t] = st ? (int64_t)(ent & EC_NODE) * ND : -1;
-                if (p.mask) skip |= ((ent >> 28) & 7u) << (t * ND);
-#pragma unroll
-                for (int i = 0; i < ND; i++) f[t][i] = st ? p.y[yk[t] + i] : 0.0;
-            }
-            if (active) {
-                const double *S = sS + e * ES;
-#pragma unroll 2
-                for (int qq = 0; qq < NIP / 2; qq++) {
-                    const int q = h * (NIP / 2) + qq;
-#pragma unroll
-                    for (int k = 0; k < ND; k++) {
-                        double s[ND], d_[TA];
-#pragma unroll
-                        for (int i = 0; i < ND; i++) s[i] = S[q * SQ + k * ND + i];
-#pragma unroll
-                        for (int t = 0; t < TA; t++) d_[t] = sdN[q * QS + k * NN + a0 + t];
-#pragma unroll
-                        for (int t = 0; t < TA; t++)
-#pragma unroll
-                            for (int i = 0; i < ND; i++) f[t][i] += d_[t] * s[i];
-                    }
-                    if (MASS) {
-                        double mv[ND];
-#pragma unroll
-                        for (int i = 0; i < ND; i++) mv[i] = S[q * SQ + ND * ND + i];
-#pragma unroll
-                        for (int t = 0; t < TA; t++) {
-                            const double n = sNf[q * NN + a0 + t];
-#pragma unroll
-                            for (int i = 0; i < ND; i++) f[t][i] += n * mv[i];
-                        }
-                    }
-                }
-            }
-#pragma unroll
-            for (int t = 0; t < TA; t++)
-#pragma unroll
-                for (int i = 0; i < ND; i++) {
-                    const double tot = f[t][i] + __shfl_xor_sync(0xffffffffu, f[t][i], 1);
-                    if (yk[t] >= 0 && !((skip >> (t * ND + i)) & 1u)) p.y[yk[t] + i] = tot;
-                }
-        }
-    }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    if (p.dot) {
-        block_sum<1, NT>(dsum);
-        if (publish_partials<1>(dsum, p.partial, &p.scal->counter[0])) {
-            sum_partials<1, NT>(dsum, p.partial);
-            if (threadIdx.x == 0) {
-                const double acc = p.first ? dsum[0] : p.scal->pq + dsum[0];   // colours are summed in launch order
-                p.scal->pq = acc;
-                p.scal->acc[0] = acc;   // multi-GPU: all-reduced in place after the last colour
-                if (p.last && p.finalize) {
-                    if (!(acc > 0.0)) p.scal->done = 3;   // not SPD / breakdown
-                    p.scal->alpha = p.scal->rz_old / acc;
-                }
-            }
-        }
-    }
-}
 
 // econn / einfo of a batch (once per handle)
 __global__ void k_ebe_econn(int64_t n, int nd, int64_t nowned, const int32_t *__restrict__ conn, const uint8_t *__restrict__ fixed,
@@ -515,35 +229,26 @@ int ebe_mma_configure(amaru_model *m) {
     return m->nsm * std::max(1, std::min(std::min(occ0, occ1), 8));
 }
 
+// cooperative launch: the colour loop of k_ebe_mma synchronises the whole grid, every CTA must be resident
 template <int NN, int ND, int NIP>
 void ebe_mma_launch(amaru_model *m, const EbeArgs &a, int grid, bool mass) {
-    if (mass) k_ebe_mma<NN, ND, NIP, true><<<grid, 128, MmaLayout<NN, ND, NIP, true>::bytes, m->stream>>>(a);
-    else k_ebe_mma<NN, ND, NIP, false><<<grid, 128, MmaLayout<NN, ND, NIP, false>::bytes, m->stream>>>(a);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(128);
+    cfg.stream = m->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative;
+    attr[0].val.cooperative = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (mass) {
+        cfg.dynamicSmemBytes = MmaLayout<NN, ND, NIP, true>::bytes;
+        CUDA_CHECK(cudaLaunchKernelEx(&cfg, k_ebe_mma<NN, ND, NIP, true>, a));
+    } else {
+        cfg.dynamicSmemBytes = MmaLayout<NN, ND, NIP, false>::bytes;
+        CUDA_CHECK(cudaLaunchKernelEx(&cfg, k_ebe_mma<NN, ND, NIP, false>, a));
+    }
 }
-
-template <int NN, int ND, int NIP, int TA, int NT>
-int ebe_configure(amaru_model *m) {
-    int occ0 = 0, occ1 = 0;
-    const size_t s0 = EbeLayout<NN, ND, NIP, TA, false, NT>::bytes, s1 = EbeLayout<NN, ND, NIP, TA, true, NT>::bytes;
-    auto k0 = k_ebe_apply<NN, ND, NIP, TA, false, NT>;
-    auto k1 = k_ebe_apply<NN, ND, NIP, TA, true, NT>;
-    CUDA_CHECK(cudaFuncSetAttribute(k0, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s0));
-    CUDA_CHECK(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s1));
-    CUDA_CHECK(cudaFuncSetAttribute(k0, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    CUDA_CHECK(cudaFuncSetAttribute(k1, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ0, k0, NT, s0));
-    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ1, k1, NT, s1));
-    return m->nsm * std::max(1, std::min(std::min(occ0, occ1), 8));
-}
-
-template <int NN, int ND, int NIP, int TA>
-void ebe_launch(amaru_model *m, const EbeArgs &a, int grid, bool mass) {
-    constexpr size_t s0 = EbeLayout<NN, ND, NIP, TA, false, EBE_NT>::bytes;
-    constexpr size_t s1 = EbeLayout<NN, ND, NIP, TA, true, EBE_NT>::bytes;
-    if (mass) k_ebe_apply<NN, ND, NIP, TA, true, EBE_NT><<<grid, EBE_NT, s1, m->stream>>>(a);
-    else k_ebe_apply<NN, ND, NIP, TA, false, EBE_NT><<<grid, EBE_NT, s0, m->stream>>>(a);
-}
-
 
 // ---- patch form: geometry / tangent planes in slot order
 template <int NN, int ND, int NIP>
@@ -652,9 +357,10 @@ void ebe_patch_setup(amaru_model *m, Ebe *E, Batch &b, EbeBatch &eb, const std::
     if (const char *e = getenv("AMARU_EBE_PATCH_MINFILL")) minfill = std::atof(e);
     if (P.fill < minfill) return;
     // Patches of one 2x2x2 neighbourhood run one after the other (8 patch colours), so an application costs at least 8 patch
-    // times however many warps are idle: below ~8 patches per resident warp the colour-ordered form (one 8-element group per
-    // warp step, no serial chain) is faster — the strong-scaling regime of the multi-GPU runs.
-    int64_t minpatch = (int64_t)8 * m->nsm * 8;
+    // times however many warps are idle: below ~6 patches per resident warp the colour-ordered form (one 8-element group per
+    // warp step, no serial chain) is faster — the strong-scaling regime of the multi-GPU runs (measured on config 3: 2 GPUs,
+    // 8 200 patches per GPU: patch form 0.31 ms, colour form 0.34 ms; 250 k elements: 0.233 vs 0.199 ms).
+    int64_t minpatch = (int64_t)6 * m->nsm * 8;
     if (const char *e = getenv("AMARU_EBE_PATCH_MINPATCH")) minpatch = std::atoll(e);
     if (P.npatch < minpatch) return;
     touched.swap(t2);
@@ -717,7 +423,6 @@ void amaru_ebe_setup(amaru_model *m) {
     m->op_ebe = !(op && std::strcmp(op, "csr") == 0);
     Ebe *E = new Ebe();
     m->ebe = E;
-    if (const char *e = getenv("AMARU_EBE_MMA")) E->mma = std::atoi(e) != 0;
     if (const char *e = getenv("AMARU_EBE_PATCH")) E->want_patch = std::atoi(e) != 0;
     E->b.resize(m->batches.size());
     std::vector<uint8_t> touched((size_t)m->nnodes, 0);   // first-touch bookkeeping across the batches (launch order)
@@ -756,6 +461,8 @@ void amaru_ebe_setup(amaru_model *m) {
             continue;
         }
         CUDA_CHECK(cudaMalloc(&eb.d_geo, std::max<size_t>((size_t)np * nipb, 1) * sizeof(double)));
+        CUDA_CHECK(cudaMalloc(&eb.d_bar, 2 * sizeof(unsigned int)));
+        CUDA_CHECK(cudaMemsetAsync(eb.d_bar, 0, 2 * sizeof(unsigned int), m->stream));
         CUDA_CHECK(cudaMalloc(&eb.d_econn, std::max<size_t>((size_t)b.nelem * b.nn, 1) * sizeof(int32_t)));
         CUDA_CHECK(cudaMalloc(&eb.d_einfo, std::max<size_t>((size_t)b.nelem, 1) * sizeof(int32_t)));
         CUDA_CHECK(cudaMemsetAsync(eb.d_einfo, 0, std::max<size_t>((size_t)b.nelem, 1) * sizeof(int32_t), m->stream));
@@ -769,11 +476,11 @@ void amaru_ebe_setup(amaru_model *m) {
         const int g = (int)std::min<int64_t>((nipb + 127) / 128, (int64_t)m->nsm * 16);
 #define GEO(NN, ND, NIP) k_ebe_geometry<NN, ND, NIP><<<g, 128, 0, m->stream>>>(b.nelem, b.d_conn, m->d_coords, b.d_dNdR, b.d_w, m->th, eb.d_geo, nipb)
         switch (b.shape) {
-        case AMARU_SHAPE_QUAD4: GEO(4, 2, 4); eb.grid = ebe_configure<4, 2, 4, 2, EBE_NT>(m); eb.grid_mma = ebe_mma_configure<4, 2, 4>(m); break;
-        case AMARU_SHAPE_QUAD8: GEO(8, 2, 4); eb.grid = ebe_configure<8, 2, 4, 4, EBE_NT>(m); eb.grid_mma = ebe_mma_configure<8, 2, 4>(m); break;
-        case AMARU_SHAPE_HEX8: GEO(8, 3, 8); eb.grid = ebe_configure<8, 3, 8, 2, EBE_NT>(m); eb.grid_mma = ebe_mma_configure<8, 3, 8>(m); break;
-        case AMARU_SHAPE_HEX20: GEO(20, 3, 8); eb.grid = ebe_configure<20, 3, 8, 5, EBE_NT>(m); eb.grid_mma = ebe_mma_configure<20, 3, 8>(m); break;
-        case AMARU_SHAPE_TET10: GEO(10, 3, 4); eb.grid = ebe_configure<10, 3, 4, 5, EBE_NT>(m); eb.grid_mma = ebe_mma_configure<10, 3, 4>(m); break;
+        case AMARU_SHAPE_QUAD4: GEO(4, 2, 4); eb.grid_mma = ebe_mma_configure<4, 2, 4>(m); break;
+        case AMARU_SHAPE_QUAD8: GEO(8, 2, 4); eb.grid_mma = ebe_mma_configure<8, 2, 4>(m); break;
+        case AMARU_SHAPE_HEX8: GEO(8, 3, 8); eb.grid_mma = ebe_mma_configure<8, 3, 8>(m); break;
+        case AMARU_SHAPE_HEX20: GEO(20, 3, 8); eb.grid_mma = ebe_mma_configure<20, 3, 8>(m); break;
+        case AMARU_SHAPE_TET10: GEO(10, 3, 4); eb.grid_mma = ebe_mma_configure<10, 3, 4>(m); break;
         default: throw AmaruError{AMARU_ERR_UNSUPPORTED, "ebe: unsupported shape"};
         }
 #undef GEO
@@ -807,6 +514,7 @@ void amaru_ebe_destroy(amaru_model *m) {
         cudaFree(eb.d_geo);
         cudaFree(eb.d_econn);
         cudaFree(eb.d_einfo);
+        cudaFree(eb.d_bar);
         for (void *q : {(void *)eb.d_desc, (void *)eb.d_deps, (void *)eb.d_pinfo, (void *)eb.d_slot_elem, (void *)eb.d_elem_slot,
                         (void *)eb.d_pnodes, (void *)eb.d_lane_ids, (void *)eb.d_pgeo, (void *)eb.d_pw, (void *)eb.d_sync,
                         (void *)eb.d_epatch})
@@ -878,14 +586,16 @@ void amaru_ebe_apply(amaru_model *m, const double *x, double *y, int mask, int d
             nl++;
             continue;
         }
-        for (size_t c = 0; c + 1 < b.color_off.size(); c++) nl += b.color_off[c + 1] > b.color_off[c];
+        int ncol = 0;
+        for (size_t c = 0; c + 1 < b.color_off.size(); c++) ncol += b.color_off[c + 1] > b.color_off[c];
+        nl += (ncol + EBE_MAXCOL - 1) / EBE_MAXCOL;
     }
     EbeArgs a;
     a.dog = E->d_dog; a.w = E->d_w; a.nip_total = m->nip_total; a.sa = m->sysA; a.sb = m->sysB;
     a.x = x; a.y = y; a.mask = mask; a.nmats = m->nmats;
     a.partial = m->d_partial; a.scal = m->d_scal; a.dot = dot; a.finalize = finalize; a.check_done = check_done;
     a.first = 1;
-    a.fused = fused && E->mma;
+    a.fused = fused;
     if (a.fused) a.fz = amaru_comm_fused_args(m);
     else std::memset(&a.fz, 0, sizeof(a.fz));
     for (size_t i = 0; i < m->batches.size(); i++) {
@@ -919,37 +629,34 @@ void amaru_ebe_apply(amaru_model *m, const double *x, double *y, int mask, int d
             a.first = 0;
             continue;
         }
-        a.econn = eb.d_econn; a.einfo = eb.d_einfo; a.geo = eb.d_geo;
+        a.econn = eb.d_econn; a.einfo = eb.d_einfo; a.geo = eb.d_geo; a.bar = eb.d_bar;
         a.nipb = b.nelem * b.nip; a.ip_off = b.ip_off; a.dNdR = b.d_dNdR; a.Nf = b.d_N; a.rho = b.d_rho;
-        for (size_t c = 0; c + 1 < b.color_off.size(); c++) {
-            const int64_t n = b.color_off[c + 1] - b.color_off[c];
-            if (n <= 0) continue;
-            il++;
-            a.e_begin = b.color_off[c];
-            a.e_end = b.color_off[c + 1];
-            a.last = il == nl;
-            if (E->mma) {   // 4 warps per CTA, 8 elements per warp and group
-                const int grid = (int)std::min<int64_t>((n + 31) / 32, eb.grid_mma);
-                switch (b.shape) {
-                case AMARU_SHAPE_QUAD4: ebe_mma_launch<4, 2, 4>(m, a, grid, mass); break;
-                case AMARU_SHAPE_QUAD8: ebe_mma_launch<8, 2, 4>(m, a, grid, mass); break;
-                case AMARU_SHAPE_HEX8: ebe_mma_launch<8, 3, 8>(m, a, grid, mass); break;
-                case AMARU_SHAPE_HEX20: ebe_mma_launch<20, 3, 8>(m, a, grid, mass); break;
-                case AMARU_SHAPE_TET10: ebe_mma_launch<10, 3, 4>(m, a, grid, mass); break;
-                default: throw AmaruError{AMARU_ERR_UNSUPPORTED, "ebe: unsupported shape"};
+        // the batch's non-empty colours, EBE_MAXCOL per persistent launch (one launch for every mesh seen so far)
+        size_t c = 0;
+        const size_t nc = b.color_off.size() - 1;
+        while (c < nc) {
+            a.ncol = 0;
+            int64_t biggest = 0;
+            while (c < nc && a.ncol < EBE_MAXCOL) {
+                const int64_t n = b.color_off[c + 1] - b.color_off[c];
+                if (n > 0) {
+                    a.cb[a.ncol] = b.color_off[c];       // colour ranges are consecutive: cb[k + 1] of one is cb[k] of the next
+                    a.cb[a.ncol + 1] = b.color_off[c + 1];
+                    a.ncol++;
+                    biggest = std::max(biggest, n);
                 }
-                m->launches++;
-                a.first = 0;
-                continue;
+                c++;
             }
-            const int epb = EBE_NT / b.nip;
-            const int grid = (int)std::min<int64_t>((n + epb - 1) / epb, eb.grid);
+            if (a.ncol == 0) break;
+            il++;
+            a.last = il == nl;
+            const int grid = (int)std::min<int64_t>((biggest + 31) / 32, eb.grid_mma);   // 4 warps per CTA, 8 elements per warp step
             switch (b.shape) {
-            case AMARU_SHAPE_QUAD4: ebe_launch<4, 2, 4, 2>(m, a, grid, mass); break;
-            case AMARU_SHAPE_QUAD8: ebe_launch<8, 2, 4, 4>(m, a, grid, mass); break;
-            case AMARU_SHAPE_HEX8: ebe_launch<8, 3, 8, 2>(m, a, grid, mass); break;
-            case AMARU_SHAPE_HEX20: ebe_launch<20, 3, 8, 5>(m, a, grid, mass); break;
-            case AMARU_SHAPE_TET10: ebe_launch<10, 3, 4, 5>(m, a, grid, mass); break;
+            case AMARU_SHAPE_QUAD4: ebe_mma_launch<4, 2, 4>(m, a, grid, mass); break;
+            case AMARU_SHAPE_QUAD8: ebe_mma_launch<8, 2, 4>(m, a, grid, mass); break;
+            case AMARU_SHAPE_HEX8: ebe_mma_launch<8, 3, 8>(m, a, grid, mass); break;
+            case AMARU_SHAPE_HEX20: ebe_mma_launch<20, 3, 8>(m, a, grid, mass); break;
+            case AMARU_SHAPE_TET10: ebe_mma_launch<10, 3, 4>(m, a, grid, mass); break;
             default: throw AmaruError{AMARU_ERR_UNSUPPORTED, "ebe: unsupported shape"};
             }
             m->launches++;
@@ -1012,7 +719,7 @@ int64_t amaru_ebe_bytes(const amaru_model *m) {
 }
 
 const char *amaru_ebe_kernel(const amaru_model *m) {
-    if (m->batches.empty()) return "k_ebe_apply";
+    if (m->batches.empty()) return "k_ebe_mma";
     const Ebe *E = static_cast<const Ebe *>(m->ebe);
     if (E && E->mma && !E->b.empty() && E->b[0].patch) {
         switch (m->batches[0].shape) {
@@ -1032,12 +739,5 @@ const char *amaru_ebe_kernel(const amaru_model *m) {
         case AMARU_SHAPE_TET10: return "k_ebe_mma<10,3,4>";
         }
     }
-    switch (m->batches[0].shape) {
-    case AMARU_SHAPE_QUAD4: return "k_ebe_apply<4,2,4,2>";
-    case AMARU_SHAPE_QUAD8: return "k_ebe_apply<8,2,4,4>";
-    case AMARU_SHAPE_HEX8: return "k_ebe_apply<8,3,8,2>";
-    case AMARU_SHAPE_HEX20: return "k_ebe_apply<20,3,8,5>";
-    case AMARU_SHAPE_TET10: return "k_ebe_apply<10,3,4,5>";
-    }
-    return "k_ebe_apply";
+    return "k_ebe_mma";
 }

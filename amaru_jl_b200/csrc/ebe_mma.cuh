@@ -22,7 +22,9 @@
 //   y[node] += f              read-modify-write of 3 consecutive doubles per node; elements of a colour share no node
 // x of the group's nodes is gathered by cp.async into a double-buffered, conflict-free stage (row stride ≡ 4 mod 8 doubles);
 // J⁻¹, coef and w are read straight from global memory as 16-byte lane-contiguous loads (a warp reads 512 contiguous bytes
-// per plane), issued before contraction 1 so that their latency hides behind it.
+// per plane), issued before contraction 1 so that their latency hides behind it; so are the y entries the lane will
+// store (ld.global.cg: a colour reads rows the previous colour wrote, and the colours run inside ONE persistent
+// cooperative launch separated by a grid barrier — 8 launches of ~20 µs each were the floor of small batches).
 #pragma once
 // (included inside the unnamed namespace of ebe.cu, after EbeArgs)
 
@@ -50,9 +52,7 @@ struct MmaLayout {
     static constexpr int NW = EW * NN;                            // econn entries of one stage
     static constexpr int WARPS = 4;
     static constexpr size_t tab_doubles = (size_t)(KS2 * NT2 + KS3 * NT3) * 32;
-    static constexpr int YW = XW + 8;                             // y stage of one group (padded node columns read past a row)
-    static constexpr size_t bytes = tab_doubles * 8 + (size_t)WARPS * 2 * XW * 8 + (size_t)WARPS * 2 * YW * 8 +
-                                    (size_t)WARPS * 2 * NW * 4 + 3 * EBE_SMATS * 8;
+    static constexpr size_t bytes = tab_doubles * 8 + (size_t)WARPS * 2 * XW * 8 + (size_t)WARPS * 2 * NW * 4 + 3 * EBE_SMATS * 8;
     static_assert(NIP == 4 || NIP == 8, "lane <-> integration point mapping needs 4 or 8 integration points");
 };
 
@@ -120,22 +120,43 @@ __device__ __forceinline__ double ebe_ip_algebra(const double (&G)[ND * ND], con
     return en;
 }
 
+// Grid-wide barrier of the persistent colour loop (all CTAs are resident: cooperative launch).  bar[0] counts arrivals
+// (monotonic inside one kernel), bar[1] publishes the completed generation.  Bounded: on a time-out the solve is flagged as broken
+// down instead of hanging the GPU.
+__device__ __forceinline__ void ebe_grid_barrier(unsigned int *bar, unsigned int gen, CgScalars *scal) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(&bar[0], 1u) == gen * gridDim.x - 1u) {
+            asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(bar + 1), "r"(gen) : "memory");
+        } else {
+            unsigned int v, spins = 0;
+            do {
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar + 1) : "memory");
+                if (v < gen) __nanosleep(32);
+            } while (v < gen && ++spins < (1u << 22));
+            if (v < gen) scal->done = 3;
+        }
+    }
+    __syncthreads();
+}
+
 template <int NN, int ND, int NIP, bool MASS>
-__global__ void __launch_bounds__(128) k_ebe_mma(EbeArgs p) {
+__global__ void __launch_bounds__(128, 2) k_ebe_mma(EbeArgs p) {
     if (p.check_done && p.scal->done) return;
     using L = MmaLayout<NN, ND, NIP, MASS>;
     constexpr int EW = L::EW, IPL = L::IPL, KS2 = L::KS2, NT2 = L::NT2, NG2 = L::NG2, KS3 = L::KS3, NT3 = L::NT3, RSX = L::RSX,
-                  XW = L::XW, YW = L::YW, NW = L::NW, NT = 128;
+                  XW = L::XW, NW = L::NW, NT = 128;
     constexpr int NLD = (NW + 31) / 32;                  // econn entries per lane and group
     extern __shared__ __align__(16) double msm[];
     double *sB2 = msm;                                   // [KS2][NT2][32]
     double *sB3 = sB2 + KS2 * NT2 * 32;                  // [KS3][NT3][32]
     double *sDog = sB3 + KS3 * NT3 * 32;                 // [EBE_SMATS][3]
     double *sXall = sDog + 3 * EBE_SMATS;                // [WARPS][2][ND][EW][RSX]
-    double *sYall = sXall + L::WARPS * 2 * XW;           // [WARPS][2][ND][EW][RSX] (+ pad): y of the group's nodes
-    int32_t *sNall = reinterpret_cast<int32_t *>(sYall + L::WARPS * 2 * YW);   // [WARPS][2][EW][NN]
+    int32_t *sNall = reinterpret_cast<int32_t *>(sXall + L::WARPS * 2 * XW);   // [WARPS][2][EW][NN]
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int er = lane >> 2, j = lane & 3;              // this lane's element of the group / position in the quad
+    __shared__ int s_last;
 
     // ---- constant operand fragments (same for every element): B2[a][col], B3[ip slot][a]
     for (int f = tid; f < KS2 * NT2 * 32; f += NT) {
@@ -166,225 +187,237 @@ __global__ void __launch_bounds__(128) k_ebe_mma(EbeArgs p) {
     if (smats)
         for (int i = tid; i < 3 * p.nmats; i += NT) sDog[i] = p.dog[i];
     double *sX = sXall + wid * 2 * XW;
-    double *sY = sYall + wid * 2 * YW;
     int32_t *sN = sNall + wid * 2 * NW;
     for (int i = lane; i < 2 * XW; i += 32) sX[i] = 0.0;  // padded node columns stay zero for the whole kernel
-    for (int i = lane; i < 2 * YW; i += 32) sY[i] = 0.0;
     unsigned long long halo_epoch = 0;
-    if (p.fused) {   // ghost entries of x: every neighbour's push of this exchange has landed (flags in the local window);
-        // every colour launch checks (the later ones find the flags raised), the last launch's last CTA advances the epoch
+    if (p.fused) {   // ghost entries of x: every neighbour's push of this exchange has landed (flags in the local window)
         halo_epoch = *reinterpret_cast<volatile unsigned long long *>(&p.fz.pd.win[p.fz.pd.rank]->halo_epoch) + 1ull;
         if (tid < p.fz.nneigh) p2p_wait(p.fz.pd, &p.fz.pd.win[p.fz.pd.rank]->hflag[p.fz.neigh[tid]], halo_epoch);
     }
     __syncthreads();
 
     double dsum[1] = {0.0};
-    const int64_t ngroups = (p.e_end - p.e_begin + EW - 1) / EW;
     const int64_t stride = (int64_t)gridDim.x * L::WARPS;
-    int32_t nreg[NLD];
-    auto load_conn = [&](int64_t g) {
-        const int64_t ge = p.e_begin + g * EW;
+    // ---- the element colours of the batch, one after the other (elements of a colour share no node); a grid-wide barrier
+    // separates two colours: the rows a colour wrote are read by the next one (through L2: ld.global.cg / st.global.cg)
+    for (int col = 0; col < p.ncol; col++) {
+        const int64_t e_begin = p.cb[col], e_end = p.cb[col + 1];
+        const int64_t ngroups = (e_end - e_begin + EW - 1) / EW;
+        int32_t nreg[NLD];
+        auto load_conn = [&](int64_t g) {
+            const int64_t ge = e_begin + g * EW;
 #pragma unroll
-        for (int t = 0; t < NLD; t++) {
-            const int i = lane + t * 32;
-            nreg[t] = (g < ngroups && i < NW && ge * NN + i < p.e_end * NN) ? p.econn[ge * NN + i] : -1;
-        }
-    };
-    auto issue_copies = [&](int buf) {                   // x of the nodes in nreg -> stage buf (rows past the end: zero)
+            for (int t = 0; t < NLD; t++) {
+                const int i = lane + t * 32;
+                nreg[t] = (g < ngroups && i < NW && ge * NN + i < e_end * NN) ? p.econn[ge * NN + i] : -1;
+            }
+        };
+        auto issue_copies = [&](int buf) {               // x of the nodes in nreg -> stage buf (rows past the end: zero)
 #pragma unroll
-        for (int t = 0; t < NLD; t++) {
-            const int i = lane + t * 32;
-            if (i < NW) {
-                const int e = i / NN, a = i - e * NN;
-                const int32_t ent = nreg[t];
-                sN[buf * NW + i] = ent;
-                double *dst = sX + buf * XW + e * RSX + a;
-                if (ent != -1) {
-                    const double *src = p.x + (int64_t)((uint32_t)ent & EC_NODE) * ND;
-                    const uint32_t d32 = (uint32_t)__cvta_generic_to_shared(dst);
-#pragma unroll
-                    for (int d = 0; d < ND; d++)
-                        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d32 + (uint32_t)(d * EW * RSX) * 8u), "l"(src + d) : "memory");
-                    // y of the node, one group ahead as well: the elements of a colour launch share no node, so nobody writes
-                    // these rows before this warp adds to them (the previous colour was another launch: L1 holds nothing stale)
-                    if (!((uint32_t)ent >> 31)) {
-                        const double *ysrc = p.y + (int64_t)((uint32_t)ent & EC_NODE) * ND;
-                        const uint32_t y32 = (uint32_t)__cvta_generic_to_shared(sY + buf * YW + e * RSX + a);
+            for (int t = 0; t < NLD; t++) {
+                const int i = lane + t * 32;
+                if (i < NW) {
+                    const int e = i / NN, a = i - e * NN;
+                    const int32_t ent = nreg[t];
+                    sN[buf * NW + i] = ent;
+                    double *dst = sX + buf * XW + e * RSX + a;
+                    if (ent != -1) {
+                        const double *src = p.x + (int64_t)((uint32_t)ent & EC_NODE) * ND;
+                        const uint32_t d32 = (uint32_t)__cvta_generic_to_shared(dst);
 #pragma unroll
                         for (int d = 0; d < ND; d++)
-                            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(y32 + (uint32_t)(d * EW * RSX) * 8u), "l"(ysrc + d) : "memory");
+                            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d32 + (uint32_t)(d * EW * RSX) * 8u), "l"(src + d) : "memory");
+                    } else {
+#pragma unroll
+                        for (int d = 0; d < ND; d++) dst[d * EW * RSX] = 0.0;
                     }
-                } else {
-#pragma unroll
-                    for (int d = 0; d < ND; d++) dst[d * EW * RSX] = 0.0;
                 }
             }
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-    };
-    int64_t g = (int64_t)blockIdx.x * L::WARPS + wid;
-    load_conn(g);
-    issue_copies(0);
-    load_conn(g + stride);
-    auto load_einfo = [&](int64_t gg) -> int {           // record of this lane's element in group gg (0 past the end)
-        const int64_t e = p.e_begin + gg * EW + er;
-        return (gg < ngroups && e < p.e_end) ? p.einfo[e] : 0;
-    };
-    int ei_next = load_einfo(g);
-    int buf = 0;
-    for (; g < ngroups; g += stride, buf ^= 1) {
-        const int64_t e0 = p.e_begin + g * EW;
-        const int ne = (int)min((int64_t)EW, p.e_end - e0);
-        const bool act = er < ne;                        // this lane's element exists
-        // ---- geometry / tangent of this lane's integration points: issued first, consumed after contraction 1
-        const int64_t ipl = (e0 + er) * NIP + j * IPL;   // first IP of the lane inside the batch
-        double Ji[IPL][ND * ND], coef[IPL], wv[IPL][6];
-        const int ei = ei_next;                          // loaded one group ago
-        ei_next = load_einfo(g + stride);
-        if (act) {
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        auto load_einfo = [&](int64_t gg) -> int {       // record of this lane's element in group gg (0 past the end)
+            const int64_t e = e_begin + gg * EW + er;
+            return (gg < ngroups && e < e_end) ? p.einfo[e] : 0;
+        };
+        int64_t g = (int64_t)blockIdx.x * L::WARPS + wid;
+        __syncwarp();                                    // the stages of the previous colour are free
+        load_conn(g);
+        issue_copies(0);
+        load_conn(g + stride);
+        int ei_next = load_einfo(g);
+        int buf = 0;
+        for (; g < ngroups; g += stride, buf ^= 1) {
+            const int64_t e0 = e_begin + g * EW;
+            const int ne = (int)min((int64_t)EW, e_end - e0);
+            const bool act = er < ne;                    // this lane's element exists
+            // ---- geometry / tangent of this lane's integration points: issued first, consumed after contraction 1
+            const int64_t ipl = (e0 + er) * NIP + j * IPL;   // first IP of the lane inside the batch
+            double Ji[IPL][ND * ND], coef[IPL], wv[IPL][6];
+            const int ei = ei_next;                      // loaded one group ago
+            ei_next = load_einfo(g + stride);
+            if (act) {
 #pragma unroll
-            for (int k = 0; k < ND * ND + 1; k++) {
-                const double *src = p.geo + (int64_t)k * p.nipb + ipl;
-                if constexpr (IPL == 2) {
-                    const double2 v = __ldcs(reinterpret_cast<const double2 *>(src));
-                    if (k < ND * ND) { Ji[0][k] = v.x; Ji[1][k] = v.y; } else { coef[0] = v.x; coef[1] = v.y; }
-                } else {
-                    const double v = __ldcs(src);
-                    if (k < ND * ND) Ji[0][k] = v; else coef[0] = v;
+                for (int k = 0; k < ND * ND + 1; k++) {
+                    const double *src = p.geo + (int64_t)k * p.nipb + ipl;
+                    if constexpr (IPL == 2) {
+                        const double2 v = __ldcs(reinterpret_cast<const double2 *>(src));
+                        if (k < ND * ND) { Ji[0][k] = v.x; Ji[1][k] = v.y; } else { coef[0] = v.x; coef[1] = v.y; }
+                    } else {
+                        const double v = __ldcs(src);
+                        if (k < ND * ND) Ji[0][k] = v; else coef[0] = v;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int h = 0; h < IPL; h++) {
+                    coef[h] = 0.0;
+#pragma unroll
+                    for (int k = 0; k < ND * ND; k++) Ji[h][k] = 0.0;
                 }
             }
-        } else {
+            const bool plastic = act && (ei & EI_PLASTIC) != 0;
+            if (plastic) {
+#pragma unroll
+                for (int c = 0; c < 6; c++) {
+                    const double *src = p.w + (int64_t)c * p.nip_total + p.ip_off + ipl;
+                    if constexpr (IPL == 2) {
+                        const double2 v = __ldcs(reinterpret_cast<const double2 *>(src));
+                        wv[0][c] = v.x; wv[1][c] = v.y;
+                    } else {
+                        wv[0][c] = __ldcs(src);
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int h = 0; h < IPL; h++)
+#pragma unroll
+                    for (int c = 0; c < 6; c++) wv[h][c] = 0.0;
+            }
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            __syncwarp();                                // stage `buf` is complete; everybody left the previous group
+            // ---- y of the nodes this lane will store: issued now, consumed by contraction 2 (the latency hides behind
+            // contraction 1); unconditional loads (row 0 for lanes that store nothing): no select in front of mma.sync
+            double F[ND][NT3][2];
+            int64_t yk[NT3][2];
+            uint32_t skip = 0;
+#pragma unroll
+            for (int n = 0; n < NT3; n++)
+#pragma unroll
+                for (int c = 0; c < 2; c++) {
+                    const int a = 8 * n + 2 * j + c;
+                    const uint32_t ent = (act && a < NN) ? (uint32_t)sN[buf * NW + er * NN + a] : 0x80000000u;
+                    const bool st = !(ent >> 31);        // ghost rows belong to the neighbour rank
+                    yk[n][c] = st ? (int64_t)(ent & EC_NODE) * ND : -1;
+                    if (p.mask) skip |= ((ent >> 28) & 7u) << ((n * 2 + c) * ND);
+                    const double *ysrc = p.y + (st ? yk[n][c] : 0);
+#pragma unroll
+                    for (int i = 0; i < ND; i++) F[i][n][c] = __ldcg(ysrc + i);
+                }
+            issue_copies(buf ^ 1);                       // nreg holds the entries of group g + stride
+            load_conn(g + 2 * stride);
+
+            // ---- contraction 1: C[i][n] += A(x; m-tile i, step s) · B2[s][n]
+            double C[ND][NT2][2];
+#pragma unroll
+            for (int i = 0; i < ND; i++)
+#pragma unroll
+                for (int n = 0; n < NT2; n++) C[i][n][0] = C[i][n][1] = 0.0;
+            const double *xa = sX + buf * XW + er * RSX + j;
+#pragma unroll
+            for (int s = 0; s < KS2; s++) {
+                double b[NT2];
+#pragma unroll
+                for (int n = 0; n < NT2; n++) b[n] = sB2[(s * NT2 + n) * 32 + lane];
+#pragma unroll
+                for (int i = 0; i < ND; i++) {
+                    const double a = xa[i * EW * RSX + 4 * s];
+#pragma unroll
+                    for (int n = 0; n < NT2; n++) dmma(C[i][n][0], C[i][n][1], a, b[n]);
+                }
+            }
+            // ---- per-IP algebra in registers
+            const double *dg = (smats ? sDog : p.dog) + 3 * (ei & EI_MAT);
+            const double dd = dg[0], oo = dg[1], gg = dg[2];
+            double S[IPL][ND * ND], mv[IPL][ND];
+            const double rho = (MASS && act) ? p.rho[e0 + er] : 0.0;
+            double en = 0.0;
 #pragma unroll
             for (int h = 0; h < IPL; h++) {
-                coef[h] = 0.0;
+                double G[ND * ND], ub[ND];
 #pragma unroll
-                for (int k = 0; k < ND * ND; k++) Ji[h][k] = 0.0;
+                for (int i = 0; i < ND; i++) {
+#pragma unroll
+                    for (int k = 0; k < ND; k++) G[i * ND + k] = NIP == 8 ? C[i][k][h] : C[i][k >> 1][k & 1];
+                    if constexpr (MASS) ub[i] = C[i][NG2][NIP == 8 ? h : 0];
+                    else ub[i] = 0.0;
+                }
+                en += ebe_ip_algebra<ND, MASS>(G, Ji[h], coef[h], plastic, wv[h], dd, oo, gg, p.sa, coef[h] * p.sb * rho, ub, S[h], mv[h]);
             }
-        }
-        const bool plastic = act && (ei & EI_PLASTIC) != 0;
-        if (plastic) {
+            dsum[0] += (p.dot && act && ei >= 0) ? en : 0.0;   // bit 31 of the record: the element belongs to another rank
+            // ---- contraction 2: F[i][n] += A(S; step (k,h), m-tile i) · B3[step][n]; the accumulators started from y
 #pragma unroll
-            for (int c = 0; c < 6; c++) {
-                const double *src = p.w + (int64_t)c * p.nip_total + p.ip_off + ipl;
-                if constexpr (IPL == 2) {
-                    const double2 v = __ldcs(reinterpret_cast<const double2 *>(src));
-                    wv[0][c] = v.x; wv[1][c] = v.y;
-                } else {
-                    wv[0][c] = __ldcs(src);
+            for (int s = 0; s < KS3; s++) {
+                const int k = s / IPL, h = s - k * IPL;
+                double b[NT3];
+#pragma unroll
+                for (int n = 0; n < NT3; n++) b[n] = sB3[(s * NT3 + n) * 32 + lane];
+#pragma unroll
+                for (int i = 0; i < ND; i++) {
+                    const double a = k < ND ? S[h][(k < ND ? k : 0) * ND + i] : mv[h][i];
+#pragma unroll
+                    for (int n = 0; n < NT3; n++) dmma(F[i][n][0], F[i][n][1], a, b[n]);
                 }
             }
-        } else {
 #pragma unroll
-            for (int h = 0; h < IPL; h++)
+            for (int n = 0; n < NT3; n++)
 #pragma unroll
-                for (int c = 0; c < 6; c++) wv[h][c] = 0.0;
+                for (int c = 0; c < 2; c++)
+                    if (yk[n][c] >= 0) {
+#pragma unroll
+                        for (int i = 0; i < ND; i++)
+                            if (!((skip >> ((n * 2 + c) * ND + i)) & 1u)) __stcg(p.y + yk[n][c] + i, F[i][n][c]);
+                    }
         }
         asm volatile("cp.async.wait_group 0;" ::: "memory");
-        __syncwarp();                                    // stage `buf` is complete; everybody left the previous group
-        issue_copies(buf ^ 1);                           // nreg holds the entries of group g + stride
-        load_conn(g + 2 * stride);
-
-        // ---- contraction 1: C[i][n] += A(x; m-tile i, step s) · B2[s][n]
-        double C[ND][NT2][2];
-#pragma unroll
-        for (int i = 0; i < ND; i++)
-#pragma unroll
-            for (int n = 0; n < NT2; n++) C[i][n][0] = C[i][n][1] = 0.0;
-        const double *xa = sX + buf * XW + er * RSX + j;
-#pragma unroll
-        for (int s = 0; s < KS2; s++) {
-            double b[NT2];
-#pragma unroll
-            for (int n = 0; n < NT2; n++) b[n] = sB2[(s * NT2 + n) * 32 + lane];
-#pragma unroll
-            for (int i = 0; i < ND; i++) {
-                const double a = xa[i * EW * RSX + 4 * s];
-#pragma unroll
-                for (int n = 0; n < NT2; n++) dmma(C[i][n][0], C[i][n][1], a, b[n]);
-            }
-        }
-        // ---- per-IP algebra in registers
-        const double *dg = (smats ? sDog : p.dog) + 3 * (ei & EI_MAT);
-        const double dd = dg[0], oo = dg[1], gg = dg[2];
-        double S[IPL][ND * ND], mv[IPL][ND];
-        const double rho = (MASS && act) ? p.rho[e0 + er] : 0.0;
-        double en = 0.0;
-#pragma unroll
-        for (int h = 0; h < IPL; h++) {
-            double G[ND * ND], ub[ND];
-#pragma unroll
-            for (int i = 0; i < ND; i++) {
-#pragma unroll
-                for (int k = 0; k < ND; k++) G[i * ND + k] = NIP == 8 ? C[i][k][h] : C[i][k >> 1][k & 1];
-                if constexpr (MASS) ub[i] = C[i][NG2][NIP == 8 ? h : 0];
-                else ub[i] = 0.0;
-            }
-            en += ebe_ip_algebra<ND, MASS>(G, Ji[h], coef[h], plastic, wv[h], dd, oo, gg, p.sa, coef[h] * p.sb * rho, ub, S[h], mv[h]);
-        }
-        if (p.dot && act && ei >= 0) dsum[0] += en;      // bit 31 of the record: the element belongs to another rank
-        // ---- contraction 2: F[i][n] += A(S; step (k,h), m-tile i) · B3[step][n]; the accumulators start from y
-        double F[ND][NT3][2];
-        int64_t yk[NT3][2];
-        uint32_t skip = 0;
-        const double *ya = sY + buf * YW + er * RSX;
-#pragma unroll
-        for (int n = 0; n < NT3; n++)
-#pragma unroll
-            for (int c = 0; c < 2; c++) {
-                const int a = 8 * n + 2 * j + c;
-                const uint32_t ent = (act && a < NN) ? (uint32_t)sN[buf * NW + er * NN + a] : 0x80000000u;
-                const bool st = !(ent >> 31);            // ghost rows belong to the neighbour rank
-                yk[n][c] = st ? (int64_t)(ent & EC_NODE) * ND : -1;
-                if (p.mask) skip |= ((ent >> 28) & 7u) << ((n * 2 + c) * ND);
-                // unconditional read of the staged value (no lane-dependent select in front of mma.sync); rows that are not
-                // stored (ghost, padding, empty slots) may hold anything finite: the stage is zero-initialised
-#pragma unroll
-                for (int i = 0; i < ND; i++) F[i][n][c] = ya[i * EW * RSX + a];
-            }
-#pragma unroll
-        for (int s = 0; s < KS3; s++) {
-            const int k = s / IPL, h = s - k * IPL;
-            double b[NT3];
-#pragma unroll
-            for (int n = 0; n < NT3; n++) b[n] = sB3[(s * NT3 + n) * 32 + lane];
-#pragma unroll
-            for (int i = 0; i < ND; i++) {
-                const double a = k < ND ? S[h][(k < ND ? k : 0) * ND + i] : mv[h][i];
-#pragma unroll
-                for (int n = 0; n < NT3; n++) dmma(F[i][n][0], F[i][n][1], a, b[n]);
-            }
-        }
-#pragma unroll
-        for (int n = 0; n < NT3; n++)
-#pragma unroll
-            for (int c = 0; c < 2; c++)
-                if (yk[n][c] >= 0) {
-#pragma unroll
-                    for (int i = 0; i < ND; i++)
-                        if (!((skip >> ((n * 2 + c) * ND + i)) & 1u)) p.y[yk[n][c] + i] = F[i][n][c];
-                }
+        if (col + 1 < p.ncol) ebe_grid_barrier(p.bar, (unsigned int)(col + 1), p.scal);
     }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
+
+    // ---- last CTA: p·Ap (per-CTA partials summed in CTA order), CG scalars, barrier reset, fused exchanges
     if (p.dot) {
         block_sum<1, NT>(dsum);
-        if (publish_partials<1>(dsum, p.partial, &p.scal->counter[0])) {
-            sum_partials<1, NT>(dsum, p.partial);
-            if (threadIdx.x == 0) {
-                const double acc = p.first ? dsum[0] : p.scal->pq + dsum[0];   // colours are summed in launch order
-                p.scal->pq = acc;
-                p.scal->acc[0] = acc;   // multi-GPU: all-reduced in place after the last colour
-                if (p.last && p.finalize) {
-                    if (!(acc > 0.0)) p.scal->done = 3;   // not SPD / breakdown
-                    p.scal->alpha = p.scal->rz_old / acc;
-                }
-            }
-            if (p.fused && p.last) {   // this rank's p.Ap -> every rank's window (summed in rank order by the vector update)
-                __syncthreads();
-                P2PWin *me = p.fz.pd.win[p.fz.pd.rank];
-                const unsigned long long se = *reinterpret_cast<volatile unsigned long long *>(&me->scal_epoch) + 1ull;
-                if (tid < 32) p2p_push_scalars(p.fz.pd, se, p.scal->acc, 1, tid);
-                if (tid == 0) me->halo_epoch = halo_epoch;
+        if (tid == 0) p.partial[blockIdx.x] = dsum[0];
+    }
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence();
+        s_last = atomicInc(&p.scal->counter[0], gridDim.x - 1) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (p.dot) {
+        sum_partials<1, NT>(dsum, p.partial);
+        if (tid == 0) {
+            const double acc = p.first ? dsum[0] : p.scal->pq + dsum[0];   // batches are summed in launch order
+            p.scal->pq = acc;
+            p.scal->acc[0] = acc;   // multi-GPU: all-reduced after the last batch
+            if (p.last && p.finalize) {
+                if (!(acc > 0.0)) p.scal->done = 3;   // not SPD / breakdown
+                p.scal->alpha = p.scal->rz_old / acc;
             }
         }
+    }
+    if (p.fused && p.last) {   // this rank's p.Ap -> every rank's window (summed in rank order by the vector update)
+        __syncthreads();
+        P2PWin *me = p.fz.pd.win[p.fz.pd.rank];
+        if (p.dot) {
+            const unsigned long long se = *reinterpret_cast<volatile unsigned long long *>(&me->scal_epoch) + 1ull;
+            if (tid < 32) p2p_push_scalars(p.fz.pd, se, p.scal->acc, 1, tid);
+        }
+        if (tid == 0) me->halo_epoch = halo_epoch;
+    }
+    if (tid == 0) {
+        p.bar[0] = 0u;
+        p.bar[1] = 0u;
     }
 }

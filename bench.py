@@ -363,7 +363,7 @@ def main():
                 "peak_source": "profiles/fp64_peak_r2.json (DFMA microbenchmark on this pool's B200, sustained)"}
     kdesc = (("matrix-free tangent operator on the FP64 tensor cores (DMMA) + fused p.Ap, x / y of a 64-element patch in shared "
               "memory, one launch per application" if "patch" in dm.spmv_kernel else
-              "matrix-free tangent operator (DMMA) + fused p.Ap, one launch per element colour; per application")
+              "matrix-free tangent operator (DMMA) + fused p.Ap, one persistent cooperative launch over the element colours")
              if is_ebe else "TMA-streamed, warp-specialised block-CSR SpMV + p.Ap dot")
     cg_iters = [p["cg_iters"] for p in phases]
     # whole-iteration algorithmic bytes of this rank

@@ -22,4 +22,3 @@ if [ "$N" = "2" ]; then
   timeout 500 python -m pytest tests/test_gpu_group.py tests/test_gpu_multi.py -q -x > gpurun_out/r2j_group_tests_n${N}.log 2>&1; tail -5 gpurun_out/r2j_group_tests_n${N}.log; echo "group tests: $((SECONDS-t0)) s"
 fi
 timeout 300 $TR --master-port 29710 bench.py --gpus $N --steps 3 --warmup 3 > gpurun_out/bench_r2_n${N}_fused.json 2> gpurun_out/bench_r2_n${N}_fused.err; cut -c1-900 gpurun_out/bench_r2_n${N}_fused.json; tail -3 gpurun_out/bench_r2_n${N}_fused.err; echo "bench fused: $((SECONDS-t0)) s"
-AMARU_P2P_FUSED=0 timeout 300 $TR --master-port 29711 bench.py --gpus $N --steps 3 --warmup 3 > gpurun_out/bench_r2_n${N}_unfused.json 2> gpurun_out/bench_r2_n${N}_unfused.err; cut -c1-500 gpurun_out/bench_r2_n${N}_unfused.json; echo "bench unfused: $((SECONDS-t0)) s"

@@ -213,7 +213,8 @@ def test_group_output_side_loads_and_recovery(tmp_path):
     fields = {}
     for ng in (1, 2):
         mesh = Mesh(Block([[0, 0, 0], [1, 1, 1]], nx=5, ny=5, nz=5, cellshape="HEX20", tag="solids"))
-        model = FEModel(mesh, [("solids", MechSolid, VonMises, dict(E=210e6, nu=0.3, fy=240e3, H=1e6))], MechContext())
+        # (H = 2e7: with H = 1e6 the three increments do not converge under the reference's rules — the CPU oracle agrees)
+        model = FEModel(mesh, [("solids", MechSolid, VonMises, dict(E=210e6, nu=0.3, fy=240e3, H=2e7))], MechContext())
         ana = MechAnalysis(model, outdir=str(tmp_path / f"out{ng}"))
         addstage(ana, [("z==0", NodeBC(ux=0, uy=0, uz=0)), ("z==1", SurfaceBC(tz="-3e5*x")), ("z>=0", BodyC(wz=-20.0))],
                  nincs=3, nouts=1)
