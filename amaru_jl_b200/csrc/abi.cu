@@ -486,8 +486,7 @@ const char *amaru_spmv_kernel(const amaru_model *m) {
     if (m->grp) return amaru_spmv_kernel(amaru_group_part(m, 0));
     if (m->op_ebe && !m->blended) return amaru_ebe_kernel(m);
     if (m->use_sym) return m->nd == 3 ? "k_spmv_sym<3,true>" : "k_spmv_sym<2,true>";
-    if (m->use_tma) return m->spmv_ver == 2 ? (m->nd == 3 ? "k_spmv_stream2<3,true>" : "k_spmv_stream2<2,true>")
-                                            : (m->nd == 3 ? "k_spmv_stream<3,true>" : "k_spmv_stream<2,true>");
+    if (m->use_tma) return m->nd == 3 ? "k_spmv_stream2<3,true>" : "k_spmv_stream2<2,true>";
     return m->nd == 3 ? "k_spmv<3,true>" : "k_spmv<2,true>";
 }
 

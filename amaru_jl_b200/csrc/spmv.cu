@@ -33,7 +33,6 @@ namespace {
 constexpr int ROW_THREADS = 256;
 constexpr int MAX_STAGES = 8;
 constexpr int NCW = 4;                      // consumer warps per CTA (8 with 2x larger tiles measured the same: 3.11 ms)
-constexpr int STREAM_THREADS = (NCW + 1) * 32;
 constexpr int XD_MAX = 4;                   // x gathers are started xd (<= XD_MAX) tiles ahead of the contraction
 
 // ------------------------------------------------------------------------------------------------ PTX wrappers
@@ -126,221 +125,10 @@ __device__ __forceinline__ double row_reduce(double acc) {
 // Shared memory: a ring of SV value stages (the big ones) and a deeper ring of SR = SV + XD record stages
 // (record + staged x, small), so that the x gathers can run XD tiles ahead without holding value buffers hostage:
 // up to SV-1 value tiles are in TMA flight per CTA.
-template <int BS, bool DOT>
-__global__ void __launch_bounds__(STREAM_THREADS)
-k_spmv_stream(int ntiles, const SpmvTile *__restrict__ tiles, const int32_t *__restrict__ trec,
-              const double *__restrict__ A, const double *__restrict__ x, double *__restrict__ y, int mask_rows,
-              int tile_blks, int tile_rows, int xcap, int nstages, int XD, int sleep_ns, double *partial,
-              CgScalars *scal, int check_done, int finalize) {
-    if (check_done && scal->done) return;
-    constexpr int B2 = BS * BS, BPI = 32 / B2, ACT = BPI * B2, NCT = NCW * 32;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ uint64_t full_v[MAX_STAGES], empty_v[MAX_STAGES], full_r[MAX_STAGES + XD_MAX], empty_r[MAX_STAGES + XD_MAX];
-    __shared__ SpmvTile shdr[MAX_STAGES + XD_MAX];
-    const StageLayout L = stage_layout(BS, tile_blks, tile_rows, xcap);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int SV = nstages, SR = nstages + XD;
-    unsigned char *vring = smem_raw;
-    unsigned char *rring = smem_raw + (size_t)SV * L.vbytes;
-    const size_t rstride = L.rbytes + L.xbytes;
-    if (tid == 0) {
-        for (int s = 0; s < SV; s++) {
-            mbar_init(&full_v[s], 1);
-            mbar_init(&empty_v[s], NCW);
-        }
-        for (int s = 0; s < SR; s++) {
-            mbar_init(&full_r[s], 1);
-            mbar_init(&empty_r[s], NCW);
-        }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    const int first = blockIdx.x, stride = gridDim.x;
-    const int nloc = first < ntiles ? (ntiles - first + stride - 1) / stride : 0;
-    double dsum[1] = {0.0};
+// (the first version of this kernel, whose consumer warps gathered x themselves, is in the history: 3.12 ms against 2.90 ms)
 
-    if (warp == NCW) {
-        // ============================ producer warp: headers 32 ahead (one per lane); record of tile j, values of tile j-XD
-        uint64_t policy = 0;
-        asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
-        SpmvTile hcur{}, hnext{};
-        if (lane < nloc) hcur = tiles[first + lane * stride];
-        if (32 + lane < nloc) hnext = tiles[first + (32 + lane) * stride];
-        int vb0 = 0, vnb = 0;   // lane l keeps (b0, nb) of tile j: the value copy of tile j-XD reads them by shuffle
-        int psr = 0, psv = 0;   // ring positions and wait parities kept as counters (no divisions in the loop)
-        uint32_t prph = 1u, pvph = 1u;   // parity of the (use-1)-th completion of the empty barriers: 1 before first wrap
-        for (int j = 0; j < nloc + XD; j++) {
-            if (j < nloc) {
-                if ((j & 31) == 0 && j > 0) {
-                    hcur = hnext;
-                    if (j + 32 + lane < nloc) hnext = tiles[first + (j + 32 + lane) * stride];
-                }
-                SpmvTile ti;
-                ti.r0 = __shfl_sync(0xffffffffu, hcur.r0, j & 31);
-                ti.nrows = __shfl_sync(0xffffffffu, hcur.nrows, j & 31);
-                ti.b0 = __shfl_sync(0xffffffffu, hcur.b0, j & 31);
-                ti.nb = __shfl_sync(0xffffffffu, hcur.nb, j & 31);
-                ti.moff = __shfl_sync(0xffffffffu, hcur.moff, j & 31);
-                ti.nu = __shfl_sync(0xffffffffu, hcur.nu, j & 31);
-                ti.recints = __shfl_sync(0xffffffffu, hcur.recints, j & 31);
-                ti.pad = 0;
-                if (lane == (j & 31)) {
-                    vb0 = ti.b0;
-                    vnb = ti.nb;
-                }
-                if (lane == 0) {
-                    const int sr = psr;
-                    if (j >= SR) mbar_wait_backoff(&empty_r[sr], prph, (unsigned)sleep_ns);
-                    shdr[sr] = ti;
-                    const uint64_t rs = ((uint64_t)ti.recints * 4 + 15) & ~15ull;
-                    mbar_arrive_expect_tx(&full_r[sr], (uint32_t)rs);
-                    tma_bulk_g2s(rring + (size_t)sr * rstride, reinterpret_cast<const unsigned char *>(trec + ti.moff),
-                                 (uint32_t)rs, &full_r[sr], policy);
-                }
-                if (++psr == SR) {
-                    psr = 0;
-                    prph ^= 1u;
-                }
-            }
-            const int jv = j - XD;
-            // (b0, nb) of tile jv were parked in lane jv&31 at most XD <= 4 iterations ago
-            const int b0 = __shfl_sync(0xffffffffu, vb0, jv & 31), nb = __shfl_sync(0xffffffffu, vnb, jv & 31);
-            if (jv >= 0 && lane == 0) {
-                const int sv = psv;
-                if (jv >= SV) mbar_wait_backoff(&empty_v[sv], pvph, (unsigned)sleep_ns);
-                const uint64_t v0 = (uint64_t)b0 * (B2 * 8), va = v0 & ~15ull;
-                const uint64_t vs = ((v0 + (uint64_t)nb * (B2 * 8) - va) + 15) & ~15ull;
-                mbar_arrive_expect_tx(&full_v[sv], (uint32_t)vs);
-                tma_bulk_g2s(vring + (size_t)sv * L.vbytes, reinterpret_cast<const unsigned char *>(A) + va, (uint32_t)vs,
-                             &full_v[sv], policy);
-            }
-            if (jv >= 0 && ++psv == SV) {
-                psv = 0;
-                pvph ^= 1u;
-            }
-            __syncwarp();
-        }
-    } else {
-        // ============================ consumer warps
-        const int ctid = tid;   // 0 .. NCT-1
-        // lane (b, r): row r of block-in-step b.  A warp step covers BPS blocks: 10 (3x3, lanes 0..29) or 16 (2x2).
-        constexpr int BPS = 32 / BS;
-        const int b = lane / BS, r = lane - b * BS;
-        const bool act = lane < BPS * BS;
-        const bool writer = lane < BS;
-        // x entries of tile j -> its record stage, asynchronously (cp.async, 8 B per copy, no registers held)
-        // one thread per unique column node: nd cp.async of 8 B each
-        int gs = 0;              // record stage / phase of the next tile to gather (incremented, no divisions)
-        uint32_t gph = 0;
-        auto gather_async = [&]() {
-            mbar_wait(&full_r[gs], gph);
-            const int nrows_j = shdr[gs].nrows, nu_j = shdr[gs].nu;
-            unsigned char *bj = rring + (size_t)gs * rstride;
-            const int32_t *ucol = reinterpret_cast<const int32_t *>(bj) + nrows_j + 1;
-            const uint32_t sxa = smem_u32(bj + L.rbytes);
-            for (int k = ctid; k < nu_j; k += NCT) {
-                const double *src = x + (int64_t)ucol[k] * BS;
-                const uint32_t dst = sxa + (uint32_t)k * (BS * 8u);
-#pragma unroll
-                for (int d = 0; d < BS; d++)
-                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + d * 8u), "l"(src + d) : "memory");
-            }
-            if (++gs == SR) {
-                gs = 0;
-                gph ^= 1u;
-            }
-        };
-        for (int d = 0; d < XD; d++) {   // prologue: gathers of the first XD tiles, one commit group per tile
-            if (d < nloc) gather_async();
-            asm volatile("cp.async.commit_group;" ::: "memory");
-        }
-        int sr = 0, sv = 0;
-        uint32_t vph = 0;
-        for (int i = 0; i < nloc; i++) {
-            // start the gathers of tile i+XD (SV >= 2: every consumer has finished tile i+XD-SR = i-SV by now)
-            if (i + XD < nloc) gather_async();
-            asm volatile("cp.async.commit_group;" ::: "memory");
-            cp_async_wait_dyn(XD);   // own gathers of tile i have landed ...
-            consumer_sync();         // ... and everybody else's
-            const int h_r0 = shdr[sr].r0, h_nrows = shdr[sr].nrows, h_b0 = shdr[sr].b0, h_nu = shdr[sr].nu;
-            const unsigned char *rb = rring + (size_t)sr * rstride;
-            const int32_t *rec = reinterpret_cast<const int32_t *>(rb);
-            const uint16_t *sl = reinterpret_cast<const uint16_t *>(rec + h_nrows + 1 + h_nu);
-            const double *sx = reinterpret_cast<const double *>(rb + L.rbytes);
-            mbar_wait(&full_v[sv], vph);
-            const double *sval = reinterpret_cast<const double *>(vring + (size_t)sv * L.vbytes + (((uint64_t)h_b0 * (B2 * 8)) & 15ull));
-            for (int lr = warp; lr < h_nrows; lr += NCW) {
-                const int32_t e0 = rec[lr], e1 = rec[lr + 1];
-                const int k0 = e0 & 0xffff, nbr = (e1 & 0xffff) - k0;
-                // lane (b, r) contracts row r of blocks k0+b, k0+b+BPS, ...: BS values (contiguous) times the BS x
-                // entries of the block column (lcol holds (local column)*BS; the BS lanes of a block share them).
-                const double *pv = sval + (k0 + b) * B2 + r * BS;
-                const uint16_t *pl = sl + k0 + b;
-                const int nfull = nbr / BPS, rem = nbr - nfull * BPS;
-                double acc0 = 0.0, acc1 = 0.0;
-                if (act) {
-                    int s = 0;
-                    for (; s + 2 <= nfull; s += 2) {
-                        const double *x0 = sx + pl[0], *x1 = sx + pl[BPS];
-#pragma unroll
-                        for (int j = 0; j < BS; j++) {
-                            acc0 += pv[j] * x0[j];
-                            acc1 += pv[BPS * B2 + j] * x1[j];
-                        }
-                        pl += 2 * BPS;
-                        pv += 2 * BPS * B2;
-                    }
-                    if (s < nfull) {
-                        const double *x0 = sx + pl[0];
-#pragma unroll
-                        for (int j = 0; j < BS; j++) acc0 += pv[j] * x0[j];
-                        pl += BPS;
-                        pv += BPS * B2;
-                    }
-                    if (b < rem) {
-                        const double *x0 = sx + pl[0];
-#pragma unroll
-                        for (int j = 0; j < BS; j++) acc1 += pv[j] * x0[j];
-                    }
-                }
-                // sum over the block lanes of each row r; result in lanes 0..BS-1
-                double tot = acc0 + acc1;
-                if constexpr (BS == 3) {
-                    const double s1 = tot + __shfl_down_sync(0xffffffffu, tot, 15);   // b < 5: S_b = a_b + a_{b+5}
-                    const double u = s1 + __shfl_down_sync(0xffffffffu, s1, 3);       // b = 0,2: S_b + S_{b+1}
-                    const double v = u + __shfl_down_sync(0xffffffffu, u, 6);         // b = 0: S_0..S_3
-                    tot = v + __shfl_down_sync(0xffffffffu, s1, 12);                  // + S_4
-                } else {
-                    tot += __shfl_xor_sync(0xffffffffu, tot, 2);
-                    tot += __shfl_xor_sync(0xffffffffu, tot, 4);
-                    tot += __shfl_xor_sync(0xffffffffu, tot, 8);
-                    tot += __shfl_xor_sync(0xffffffffu, tot, 16);
-                }
-                if (writer) {
-                    const int64_t idx = (int64_t)(h_r0 + lr) * BS + lane;
-                    if (mask_rows && ((e0 >> (16 + lane)) & 1)) tot = 0.0;
-                    y[idx] = tot;
-                    if (DOT && nbr > 0) dsum[0] += tot * sx[((e0 >> 19) & 0x1fff) * BS + lane];
-                }
-            }
-            __syncwarp();
-            if (lane == 0) {   // this warp is done with the value stage and with the record stage
-                mbar_arrive(&empty_v[sv]);
-                mbar_arrive(&empty_r[sr]);
-            }
-            if (++sr == SR) sr = 0;
-            if (++sv == SV) {
-                sv = 0;
-                vph ^= 1u;
-            }
-        }
-    }
-    if (DOT) spmv_dot_epilogue<STREAM_THREADS>(dsum, partial, scal, finalize);
-}
-
-// ------------------------------------------------------------------------------------------------ streamed kernel, v2
-// Same data path, but the x gather has its own warp and nothing synchronises the consumer warps with each other:
-//   warp NCW   : TMA producer (values ring SV, record ring SR), as above;
+// The x gather has its own warp and nothing synchronises the consumer warps with each other:
+//   warp NCW   : TMA producer (values ring SV, record ring SR): per tile two cp.async.bulk copies completing on `full` mbarriers;
 //   warp NCW+1 : gather warp — waits for a record, issues the cp.async copies of the tile's unique x entries and lets
 //                the copies themselves arrive on the stage's `xfull` mbarrier (cp.async.mbarrier.arrive.noinc, one
 //                arrival per lane), then moves on: it runs ahead as far as records have landed;
@@ -908,14 +696,9 @@ template <int BS, bool DOT>
 void launch_stream(amaru_model *m, const double *A, const double *x, double *y, int mask, int check_done, int finalize) {
     const StageLayout L = stage_layout(BS, m->tile_blks, m->tile_rows, m->tile_xcap);
     const size_t smem = m->spmv_stages * L.vbytes + (size_t)(m->spmv_stages + m->spmv_xd) * (L.rbytes + L.xbytes);
-    if (m->spmv_ver == 2)
-        k_spmv_stream2<BS, DOT><<<m->grid_tma, STREAM2_THREADS, smem, m->stream>>>(
-            m->ntiles, reinterpret_cast<const SpmvTile *>(m->d_tiles), m->d_tmeta, A, x, y, mask, m->tile_blks, m->tile_rows,
-            m->tile_xcap, m->spmv_stages, m->spmv_xd, m->spmv_sleep, m->d_partial, m->d_scal, check_done, finalize);
-    else
-        k_spmv_stream<BS, DOT><<<m->grid_tma, STREAM_THREADS, smem, m->stream>>>(
-            m->ntiles, reinterpret_cast<const SpmvTile *>(m->d_tiles), m->d_tmeta, A, x, y, mask, m->tile_blks, m->tile_rows,
-            m->tile_xcap, m->spmv_stages, m->spmv_xd, m->spmv_sleep, m->d_partial, m->d_scal, check_done, finalize);
+    k_spmv_stream2<BS, DOT><<<m->grid_tma, STREAM2_THREADS, smem, m->stream>>>(
+        m->ntiles, reinterpret_cast<const SpmvTile *>(m->d_tiles), m->d_tmeta, A, x, y, mask, m->tile_blks, m->tile_rows,
+        m->tile_xcap, m->spmv_stages, m->spmv_xd, m->spmv_sleep, m->d_partial, m->d_scal, check_done, finalize);
 }
 
 // The attribute is per function and device, and the dynamic size depends on the model's tile geometry: handles of different
@@ -928,15 +711,9 @@ bool configure_stream(amaru_model *m) {
     const size_t smem = m->spmv_stages * L.vbytes + (size_t)(m->spmv_stages + m->spmv_xd) * (L.rbytes + L.xbytes);
     if (smem > (size_t)SPMV_SMEM_CAP) return false;
     int occ = 0;
-    if (m->spmv_ver == 2) {
-        CUDA_CHECK(cudaFuncSetAttribute(k_spmv_stream2<BS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SPMV_SMEM_CAP));
-        CUDA_CHECK(cudaFuncSetAttribute(k_spmv_stream2<BS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SPMV_SMEM_CAP));
-        CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_spmv_stream2<BS, true>, STREAM2_THREADS, smem));
-    } else {
-        CUDA_CHECK(cudaFuncSetAttribute(k_spmv_stream<BS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SPMV_SMEM_CAP));
-        CUDA_CHECK(cudaFuncSetAttribute(k_spmv_stream<BS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SPMV_SMEM_CAP));
-        CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_spmv_stream<BS, true>, STREAM_THREADS, smem));
-    }
+    CUDA_CHECK(cudaFuncSetAttribute(k_spmv_stream2<BS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SPMV_SMEM_CAP));
+    CUDA_CHECK(cudaFuncSetAttribute(k_spmv_stream2<BS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SPMV_SMEM_CAP));
+    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_spmv_stream2<BS, true>, STREAM2_THREADS, smem));
     if (occ < 1) return false;
     m->grid_tma = std::min(m->nsm * occ, m->ntiles);
     return true;
@@ -1093,7 +870,7 @@ void amaru_spmv_setup(amaru_model *m) {
     m->spmv_warps = NCW;
     // defaults from the sweep on B200 at 1 M HEX20 elements (profiles/spmv_sweep_r1.txt): the consumers are issue-bound,
     // so small stages (-> 3 CTAs / 15 warps per SM) beat deeper pipelines
-    m->spmv_ver = env_int("AMARU_SPMV_V", 2);   // 2: dedicated gather warp, unsynchronised consumers; 1: consumers gather
+    m->spmv_ver = 2;
     m->spmv_xd = std::min(std::max(env_int("AMARU_SPMV_XD", m->spmv_ver == 2 ? 2 : 1), 1), XD_MAX);
     m->spmv_stages = std::min(std::max(env_int("AMARU_SPMV_STAGES", 2), 2), MAX_STAGES);
     m->tile_blks = std::min(env_int("AMARU_SPMV_TILE", bs == 3 ? 232 : 522), 8191);   // 13-bit local diagonal index
