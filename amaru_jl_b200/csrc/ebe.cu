@@ -421,6 +421,10 @@ void ebe_patch_setup(amaru_model *m, Ebe *E, Batch &b, EbeBatch &eb, const std::
 void amaru_ebe_setup(amaru_model *m) {
     const char *op = getenv("AMARU_OPERATOR");
     m->op_ebe = !(op && std::strcmp(op, "csr") == 0);
+    // Tiny systems (BASELINE configs[0]: 200 QUAD8 elements) are pure latency: the colour-ordered kernel walks through its
+    // colours one after the other (~4 us each with a handful of CTAs) while the block-CSR SpMV streams a few hundred KB in one
+    // step; unless the environment says otherwise such handles start with the CSR operator (amaru_set_operator still switches).
+    if (!op && m->nelem_total <= 1024 && 5e-6 + (double)m->nblk * m->nd * m->nd * 8.0 / 6.0e12 < 4e-6 * m->ncolors) m->op_ebe = false;
     Ebe *E = new Ebe();
     m->ebe = E;
     if (const char *e = getenv("AMARU_EBE_PATCH")) E->want_patch = std::atoi(e) != 0;

@@ -200,9 +200,9 @@ __global__ void __launch_bounds__(128, 2) k_ebe_mma(EbeArgs p) {
     const int64_t stride = (int64_t)gridDim.x * L::WARPS;
     // ---- the element colours of the batch, one after the other (elements of a colour share no node); a grid-wide barrier
     // separates two colours: the rows a colour wrote are read by the next one (through L2: ld.global.cg / st.global.cg)
+    int64_t e_begin = p.cb[0], e_end = p.cb[1], ngroups = (e_end - e_begin + EW - 1) / EW;
+    int ei_next = 0;
     for (int col = 0; col < p.ncol; col++) {
-        const int64_t e_begin = p.cb[col], e_end = p.cb[col + 1];
-        const int64_t ngroups = (e_end - e_begin + EW - 1) / EW;
         int32_t nreg[NLD];
         auto load_conn = [&](int64_t g) {
             const int64_t ge = e_begin + g * EW;
@@ -240,11 +240,16 @@ __global__ void __launch_bounds__(128, 2) k_ebe_mma(EbeArgs p) {
             return (gg < ngroups && e < e_end) ? p.einfo[e] : 0;
         };
         int64_t g = (int64_t)blockIdx.x * L::WARPS + wid;
-        __syncwarp();                                    // the stages of the previous colour are free
-        load_conn(g);
-        issue_copies(0);
+        // prologue of a colour: connectivity and x of the warp's first group (x is read-only: the prologue of colour c + 1 runs
+        // before the grid barrier that ends colour c, so its latency hides behind the wait)
+        auto prologue = [&]() {
+            __syncwarp();                                // the stages of the previous colour are free
+            load_conn(g);
+            issue_copies(0);
+            ei_next = load_einfo(g);
+        };
+        if (col == 0) prologue();
         load_conn(g + stride);
-        int ei_next = load_einfo(g);
         int buf = 0;
         for (; g < ngroups; g += stride, buf ^= 1) {
             const int64_t e0 = e_begin + g * EW;
@@ -379,7 +384,14 @@ __global__ void __launch_bounds__(128, 2) k_ebe_mma(EbeArgs p) {
                     }
         }
         asm volatile("cp.async.wait_group 0;" ::: "memory");
-        if (col + 1 < p.ncol) ebe_grid_barrier(p.bar, (unsigned int)(col + 1), p.scal);
+        if (col + 1 < p.ncol) {
+            e_begin = p.cb[col + 1];
+            e_end = p.cb[col + 2];
+            ngroups = (e_end - e_begin + EW - 1) / EW;
+            g = (int64_t)blockIdx.x * L::WARPS + wid;
+            prologue();
+            ebe_grid_barrier(p.bar, (unsigned int)(col + 1), p.scal);
+        }
     }
 
     // ---- last CTA: p·Ap (per-CTA partials summed in CTA order), CG scalars, barrier reset, fused exchanges

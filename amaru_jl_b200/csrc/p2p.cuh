@@ -82,12 +82,16 @@ __device__ __forceinline__ void p2p_push_scalars(const P2PDev &pd, unsigned long
         st_release_sys(&w->sflag[par][pd.rank], epoch);
     }
 }
-// one thread; out[0..n) = sum over ranks in rank order; false on time-out / abort
+// first warp of a CTA (all 32 lanes): lane r waits for rank r's flag (the waits overlap), then every lane forms the sum
+// over the ranks in rank order; out[0..n) valid in every lane; false on time-out / abort
 __device__ __forceinline__ bool p2p_collect(const P2PDev &pd, unsigned long long epoch, double *out, int n) {
     P2PWin *me = pd.win[pd.rank];
     const int par = (int)(epoch & 1ull);
-    for (int r = 0; r < pd.nranks; r++)
-        if (!p2p_wait(pd, &me->sflag[par][r], epoch)) return false;
+    const int lane = threadIdx.x & 31;
+    bool ok = true;
+    if (lane < pd.nranks) ok = p2p_wait(pd, &me->sflag[par][lane], epoch);
+    ok = __all_sync(0xffffffffu, ok);
+    if (!ok) return false;
     for (int k = 0; k < n; k++) {
         double s = *reinterpret_cast<volatile double *>(&me->slot[par][0][k]);
         for (int r = 1; r < pd.nranks; r++) s += *reinterpret_cast<volatile double *>(&me->slot[par][r][k]);

@@ -152,10 +152,13 @@ k_cg_update_f(int64_t nnodes, const double *__restrict__ p, const double *__rest
     __shared__ int s_ok;
     P2PWin *me = fz.pd.win[fz.pd.rank];
     const unsigned long long base = *reinterpret_cast<volatile unsigned long long *>(&me->scal_epoch);
-    if (threadIdx.x == 0) {
+    if (threadIdx.x < 32) {
         double v[1] = {0.0};
-        s_ok = p2p_collect(fz.pd, base + 1, v, 1) ? 1 : 0;
-        s_pq = v[0];
+        const bool ok = p2p_collect(fz.pd, base + 1, v, 1);
+        if (threadIdx.x == 0) {
+            s_ok = ok ? 1 : 0;
+            s_pq = v[0];
+        }
     }
     __syncthreads();
     if (!s_ok) return;                                   // a peer left the sequence: the host reports AMARU_ERR_COMM
@@ -206,11 +209,14 @@ k_cg_pupdate_f(int64_t nnodes, const double *__restrict__ z, double *p, CgScalar
     P2PWin *me = fz.pd.win[fz.pd.rank];
     const unsigned long long base = *reinterpret_cast<volatile unsigned long long *>(&me->scal_epoch);
     const unsigned long long he = *reinterpret_cast<volatile unsigned long long *>(&me->halo_epoch) + 1ull;
-    if (threadIdx.x == 0) {
+    if (threadIdx.x < 32) {
         double v[2] = {0.0, 0.0};
-        s_ok = p2p_collect(fz.pd, base + 1, v, 2) ? 1 : 0;
-        s_v[0] = v[0];
-        s_v[1] = v[1];
+        const bool ok = p2p_collect(fz.pd, base + 1, v, 2);
+        if (threadIdx.x == 0) {
+            s_ok = ok ? 1 : 0;
+            s_v[0] = v[0];
+            s_v[1] = v[1];
+        }
     }
     __syncthreads();
     if (!s_ok) return;

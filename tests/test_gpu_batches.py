@@ -17,6 +17,19 @@ from oracle import oracle as O
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True, params=["ebe-patch", "ebe-colour", "csr"])
+def cg_operator(request, monkeypatch):
+    """Multi-batch handles with every CG operator: the patch form of the matrix-free operator (forced on these small meshes),
+    its colour-ordered form, and the block-CSR SpMV (what handles this small start with)."""
+    monkeypatch.setenv("AMARU_OPERATOR", "csr" if request.param == "csr" else "ebe")
+    if request.param == "ebe-patch":
+        monkeypatch.setenv("AMARU_EBE_PATCH_MINFILL", "0")
+        monkeypatch.setenv("AMARU_EBE_PATCH_MINPATCH", "0")
+    elif request.param == "ebe-colour":
+        monkeypatch.setenv("AMARU_EBE_PATCH", "0")
+    return request.param
+
+
 def rel(a, b):
     d = np.abs(b).max()
     return np.abs(a - b).max() / (d if d > 0 else 1.0)
