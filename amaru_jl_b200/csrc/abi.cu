@@ -78,8 +78,10 @@ void reset_status(amaru_model *m) { CUDA_CHECK(cudaMemsetAsync(m->d_status, 0, s
 
 amaru_model *amaru_create_impl(const CreateArgs &a) {
     AMARU_REQUIRE(a.ndim == 2 || a.ndim == 3, AMARU_ERR_ARG, "amaru_create: ndim must be 2 or 3");
-    AMARU_REQUIRE(a.stressmodel == AMARU_STRESS_D3 || a.stressmodel == AMARU_STRESS_PLANESTRAIN, AMARU_ERR_UNSUPPORTED,
-                  "amaru_create: only the d3 / planestrain stress models are on the B200 hot path (no CPU fallback)");
+    AMARU_REQUIRE(a.stressmodel == AMARU_STRESS_D3 || a.stressmodel == AMARU_STRESS_PLANESTRAIN ||
+                      a.stressmodel == AMARU_STRESS_PLANESTRESS, AMARU_ERR_UNSUPPORTED,
+                  "amaru_create: only the d3 / planestrain / planestress stress models are on the B200 hot path (no CPU fallback)");
+    AMARU_REQUIRE(a.stressmodel != AMARU_STRESS_PLANESTRESS || a.ndim == 2, AMARU_ERR_ARG, "amaru_create: planestress needs ndim == 2");
     AMARU_REQUIRE(a.nnodes > 0 && a.nbatches > 0 && a.nmats > 0, AMARU_ERR_ARG, "amaru_create: empty model");
     AMARU_REQUIRE(a.coords && a.conn && a.elem_mat && a.mat_kind && a.mat_params && a.eqid && a.batch_shape &&
                       a.batch_nelem, AMARU_ERR_ARG, "amaru_create: null pointer");
@@ -92,6 +94,8 @@ amaru_model *amaru_create_impl(const CreateArgs &a) {
         const int k = a.mat_kind[i];
         AMARU_REQUIRE(k == AMARU_MAT_LINEAR_ELASTIC || k == AMARU_MAT_VON_MISES || k == AMARU_MAT_DRUCKER_PRAGER,
                       AMARU_ERR_UNSUPPORTED, "amaru_create: material outside the hot path (LinearElastic, VonMises, DruckerPrager)");
+        AMARU_REQUIRE(a.stressmodel != AMARU_STRESS_PLANESTRESS || k == AMARU_MAT_LINEAR_ELASTIC, AMARU_ERR_UNSUPPORTED,
+                      "amaru_create: planestress is available for LinearElastic only (linear-elastic.jl:99-108)");
     }
 
     // on a throw below, release every device allocation made so far (not only the struct)
@@ -200,7 +204,20 @@ amaru_model *amaru_create_impl(const CreateArgs &a) {
         m->h_fixed.swap(fx);
     }
     m->d_mat_kind = upload(a.mat_kind, (size_t)a.nmats);
-    m->d_mat_par = upload(a.mat_params, (size_t)a.nmats * AMARU_MAT_NPARAMS);
+    {
+        // Plane stress (linear-elastic.jl:99-108: c = E/(1-ν²); c, cν, c(1-ν)) restricted to the in-plane components IS the
+        // 3D / plane-strain matrix of the material E* = E(1+2ν)/(1+ν)², ν* = ν/(1+ν) (same shear modulus): every kernel keeps
+        // its one constitutive form and the device gets the equivalent constants; σzz, the only place where the two differ,
+        // is cleared after every state update (amaru_update_device).
+        std::vector<double> par(a.mat_params, a.mat_params + (size_t)a.nmats * AMARU_MAT_NPARAMS);
+        if (a.stressmodel == AMARU_STRESS_PLANESTRESS)
+            for (int i = 0; i < a.nmats; i++) {
+                const double E = par[(size_t)i * AMARU_MAT_NPARAMS], nu = par[(size_t)i * AMARU_MAT_NPARAMS + 1];
+                par[(size_t)i * AMARU_MAT_NPARAMS] = E * (1.0 + 2.0 * nu) / ((1.0 + nu) * (1.0 + nu));
+                par[(size_t)i * AMARU_MAT_NPARAMS + 1] = nu / (1.0 + nu);
+            }
+        m->d_mat_par = upload(par.data(), par.size());
+    }
     m->h_eqid.assign(a.eqid, a.eqid + (size_t)a.nnodes * m->nd);
 
     // pattern + matrix

@@ -209,6 +209,10 @@ void amaru_launch_update(amaru_model *m, const double *d_dU_nodes, double *d_f_n
         default: throw AmaruError{AMARU_ERR_UNSUPPORTED, "update: unsupported shape"};
         }
     }
+    // plane stress (LinearElastic, linear-elastic.jl:99-108: the zz row of De is zero): the kernels run on the equivalent
+    // plane-strain constants (abi.cu), whose σzz = c*ν*(εxx+εyy) is the one entry that differs — cleared here
+    if (mode == 0 && m->stressmodel == AMARU_STRESS_PLANESTRESS && m->nip_total > 0)
+        CUDA_CHECK(cudaMemsetAsync(m->d_state + 2 * m->nip_total, 0, (size_t)m->nip_total * sizeof(double), m->stream));
 }
 
 void amaru_state_permute(amaru_model *m, double *d_io, int plane0, int ncomp, bool to_device) {

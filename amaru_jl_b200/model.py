@@ -154,7 +154,7 @@ class FEModel:
         ctx.ndim = mesh.ndim                                         # fe-model.jl:94
         if ctx.ndim == 3 and ctx.stressmodel not in ("d3", "none"):
             raise AmaruError("FEModel: 3D models need stressmodel d3")
-        if ctx.stressmodel in ("planestress", "axisymmetric"):
+        if ctx.stressmodel == "axisymmetric":
             raise AmaruError(f"stressmodel {ctx.stressmodel} is outside the B200 hot path (no CPU fallback)")
         self.thickness = float(thickness)
         self.ndim = ctx.ndim
@@ -188,6 +188,8 @@ class FEModel:
             self.elem_rho[sel] = props.rho
         if (self.elem_mat < 0).any():
             raise AmaruError("FEModel: some cells have no element/material binding")
+        if ctx.stressmodel == "planestress" and (self.ndim != 2 or not all(isinstance(m, LinearElastic) for m in self.materials)):
+            raise AmaruError("stressmodel planestress is on the B200 hot path for 2D LinearElastic models only (no CPU fallback)")
         self.nip = self.shape.quadrature.shape[0]
         self.nip_total = self.nelems * self.nip
         nd = self.ndim
@@ -396,7 +398,7 @@ class FEModel:
     def flatten(self):
         """Arrays exactly as amaru_create takes them (include/amaru_b200.h)."""
         return dict(
-            ndim=self.ndim, stressmodel=0 if self.ctx.stressmodel in ("d3", "none") else 1,
+            ndim=self.ndim, stressmodel={"d3": 0, "none": 0, "planestrain": 1, "planestress": 2}[self.ctx.stressmodel],
             thickness=self.thickness, coords=np.ascontiguousarray(self.coords, dtype=np.float64),
             batch_shape=np.array([self.shape.id], dtype=np.int32),
             batch_nelem=np.array([self.nelems], dtype=np.int64),

@@ -62,6 +62,9 @@ extern "C" {
 /* stress models accepted (mech-solver.jl:9): everything that uses the 3D constitutive matrix */
 #define AMARU_STRESS_D3 0
 #define AMARU_STRESS_PLANESTRAIN 1
+/* plane stress, LinearElastic only (the only material whose calcDe has that branch, linear-elastic.jl:99-108): 2D models;
+ * σzz stays zero, the in-plane moduli are c = E/(1-ν²): c, cν, c(1-ν) */
+#define AMARU_STRESS_PLANESTRESS 2
 
 /* preconditioners for the PCG that replaces lu(K11) (solver.jl:42-43) */
 #define AMARU_PRECOND_JACOBI 0

@@ -31,6 +31,7 @@
 #define MAT_LE 1
 #define MAT_VM 2
 #define MAT_DP 3
+#define MAT_LE_PS 4 /* LinearElastic under stressmodel = :planestress (oracle-side kind only) */
 #define NPAR 8
 #define MAXNN 20
 #define MAXNE 60
@@ -280,6 +281,15 @@ void orc_calcDe(double E, double nu, double *D) {
     for (int i = 3; i < 6; i++) D[6 * i + i] = c * (1.0 - 2.0 * nu);
 }
 
+/* calcDe, plane-stress branch: src/mech/mat/linear-elastic.jl:99-108 (the zz row and column are zero) */
+void orc_calcDe_ps(double E, double nu, double *D) {
+    const double c = E / (1.0 - nu * nu);
+    memset(D, 0, 36 * sizeof(double));
+    D[0] = c; D[1] = c * nu;
+    D[6] = c * nu; D[7] = c;
+    for (int i = 3; i < 6; i++) D[6 * i + i] = c * (1.0 - nu);
+}
+
 static void matvec6(const double *D, const double *x, double *y) {
     for (int i = 0; i < 6; i++) {
         double a = 0;
@@ -292,6 +302,10 @@ static void matvec6(const double *D, const double *x, double *y) {
  * returns 0 ok, 6 if the J2>0 assertion of von-mises.jl:117 fails. */
 int orc_calcD(int kind, const double *par, const double *sig, double dlam, double *D) {
     const double E = par[0], nu = par[1];
+    if (kind == MAT_LE_PS) {
+        orc_calcDe_ps(E, nu, D);
+        return 0;
+    }
     orc_calcDe(E, nu, D);
     if (kind == MAT_LE) return 0;
     if (dlam == 0.0) return 0;
@@ -343,10 +357,11 @@ int orc_update_ip(int kind, const double *par, double *sig, double *eps, double 
                   const double *deps, double *dsig) {
     const double E = par[0], nu = par[1];
     double De[36], ds[6], sini[6], str[6];
-    orc_calcDe(E, nu, De);
+    if (kind == MAT_LE_PS) orc_calcDe_ps(E, nu, De);
+    else orc_calcDe(E, nu, De);
     matvec6(De, deps, ds);
     memcpy(sini, sig, sizeof sini);
-    if (kind == MAT_LE) {
+    if (kind == MAT_LE || kind == MAT_LE_PS) {
         for (int i = 0; i < 6; i++) { eps[i] += deps[i]; sig[i] += ds[i]; dsig[i] = ds[i]; }
         return 0;
     }

@@ -107,6 +107,12 @@ def calcDe(E, nu):
     return D
 
 
+def calcDe_planestress(E, nu):
+    D = np.zeros((6, 6))
+    lib().orc_calcDe_ps(C.c_double(E), C.c_double(nu), _d(D))
+    return D
+
+
 def calcD(kind, params, sig, dlam):
     D = np.zeros((6, 6))
     p = np.zeros(8)
@@ -153,7 +159,10 @@ class OracleModel:
         self.conn = np.ascontiguousarray(flat["conn"], dtype=np.int32)
         self.nelem = self.conn.shape[0]
         self.elem_mat = np.ascontiguousarray(flat["elem_mat"], dtype=np.int32)
-        self.mat_kind = np.ascontiguousarray(flat["mat_kind"], dtype=np.int32)
+        self.mat_kind = np.ascontiguousarray(flat["mat_kind"], dtype=np.int32).copy()
+        if int(flat.get("stressmodel", 0)) == 2:   # :planestress — LinearElastic's own calcDe branch (linear-elastic.jl:99-108)
+            assert (self.mat_kind == 1).all(), "planestress: LinearElastic only"
+            self.mat_kind[:] = 4
         self.mat_par = np.ascontiguousarray(flat["mat_params"], dtype=np.float64)
         self.eqid = np.ascontiguousarray(eqid, dtype=np.int32)
         self.ndofs, self.nu = int(ndofs), int(nu)

@@ -46,7 +46,10 @@ def test_unsupported_features_are_refused_on_the_host():
     from amaru_jl_b200 import AmaruError, Block, FEModel, LinearElastic, MechContext, MechSolid, Mesh
     mesh = Mesh(Block([[0, 0], [1, 1]], nx=1, ny=1, cellshape="QUAD8", tag="s"))
     with pytest.raises(AmaruError):
-        FEModel(mesh, [("s", MechSolid, LinearElastic, dict(E=1.0, nu=0.3))], MechContext(stressmodel="planestress"))
+        FEModel(mesh, [("s", MechSolid, LinearElastic, dict(E=1.0, nu=0.3))], MechContext(stressmodel="axisymmetric"))
+    from amaru_jl_b200 import VonMises
+    with pytest.raises(AmaruError):                      # plane stress: LinearElastic only (linear-elastic.jl:99-108)
+        FEModel(mesh, [("s", MechSolid, VonMises, dict(E=1.0, nu=0.3, fy=1.0))], MechContext(stressmodel="planestress"))
     with pytest.raises(AmaruError):
         FEModel(mesh, [("s", object, LinearElastic, dict(E=1.0, nu=0.3))], MechContext())
     with pytest.raises(AmaruError):

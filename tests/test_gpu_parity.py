@@ -471,3 +471,39 @@ def test_edge_cases_single_element_all_prescribed_empty_sets():
     dFo, st = om.update_state(Uo)
     assert st == 0 and rel(dF, dFo) < 1e-12
     dm.close()
+
+
+@pytest.mark.parametrize("shape,n", [("QUAD4", 5), ("QUAD8", 4)])
+@pytest.mark.parametrize("op", ["csr", "ebe"])
+def test_plane_stress_linear_elastic(shape, n, op):
+    """stressmodel = :planestress (LinearElastic's own calcDe branch, linear-elastic.jl:99-108; AMARU_STRESS_PLANESTRESS).  The
+    device runs on the equivalent plane-strain constants and clears σzz; the oracle uses the reference's plane-stress matrix
+    literally: K bit pattern and values (1e-12), solve (1e-8), state update incl. σzz = 0 (1e-12), operator products."""
+    mesh = Mesh(Block([[0, 0], [2, 1]], nx=2 * n, ny=n, cellshape=shape, tag="solids"))
+    rng = np.random.default_rng(3)
+    c = mesh.coords
+    interior = (c[:, 0] > 1e-9) & (c[:, 0] < 2 - 1e-9) & (c[:, 1] > 1e-9) & (c[:, 1] < 1 - 1e-9)
+    c[interior, :2] += rng.uniform(-0.15, 0.15, (interior.sum(), 2)) / (2 * n + 2)
+    mesh.coords[...] = np.round(c, 8)
+    model = FEModel(mesh, [("solids", MechSolid, LinearElastic, dict(E=100.0, nu=0.3)),
+                           ("y>=0.4", MechSolid, LinearElastic, dict(E=50.0, nu=0.2))], MechContext(stressmodel="planestress"),
+                    thickness=0.7)
+    om, dm, eqid, nu, setup = pair(model, clamp_bcs(model))
+    dm.set_operator(op)
+    K = check_K(om, dm)
+    Uex, Fex = model.get_bc_vals(eqid, setup)
+    U, F = Uex.copy(), Fex.copy()
+    dm.solve(U, F, cg_rtol=1e-12)
+    Uo, Fo = Uex.copy(), Fex.copy()
+    ok, _ = O.solve_system(K, Uo, Fo, nu)
+    assert ok and rel(U, Uo) < 1e-8 and rel(F[nu:], Fo[nu:]) < 1e-8
+    x = rng.uniform(-1, 1, eqid.size)
+    y, _ = dm.operator_apply(x, masked=False)
+    assert rel(y, K @ x) < 1e-12
+    dF = dm.update_state(Uo)
+    dFo, st = om.update_state(Uo)
+    assert st == 0 and rel(dF, dFo) < 1e-12
+    s = dm.get_state()
+    assert rel(s["sigma"], om.sig) < 1e-12 and np.abs(s["sigma"][:, 2]).max() == 0.0
+    assert rel(s["eps"], om.eps) < 1e-12
+    dm.close()

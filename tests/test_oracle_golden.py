@@ -76,6 +76,26 @@ def test_elastic_quad4():
     assert np.abs(res["U"][eqid] - dis).max() < 1e-5
 
 
+def test_elastic_quad4_planestress():
+    """Plane stress (calcDe branch linear-elastic.jl:99-108) on the plate of elastic-quad4.jl: the state is uniaxial
+    (σyy = -1, σxx = σzz = 0), so uy = -1/E and ux = ν/E exactly; the in-plane block of the plane-stress matrix equals the
+    plane-strain matrix of E* = E(1+2ν)/(1+ν)², ν* = ν/(1+ν) — the identity the CUDA path relies on."""
+    mesh = Mesh(Block([[0, 0], [1, 1]], nx=2, ny=2, cellshape="QUAD8", tag="solid"))
+    model = FEModel(mesh, [("solid", MechSolid, LinearElastic, dict(E=1.0, nu=0.25))], MechContext(stressmodel="planestress"))
+    bcs = [("x==0.", SurfaceBC(ux=0.)), ("y==0.", SurfaceBC(uy=0)), ("y==1.", SurfaceBC(ty=-1.))]
+    res, eqid, om = run(model, bcs, nincs=1)
+    assert res["success"]
+    U = res["U"][eqid]
+    assert np.abs(U[:, 0] - 0.25 * model.coords[:, 0]).max() < 1e-12
+    assert np.abs(U[:, 1] + 1.0 * model.coords[:, 1]).max() < 1e-12
+    assert np.abs(om.sig - np.array([0, -1.0, 0, 0, 0, 0])).max() < 1e-12
+    E, nu = 3.7, 0.31
+    Es, nus = E * (1 + 2 * nu) / (1 + nu) ** 2, nu / (1 + nu)
+    ip = [0, 1, 5]
+    assert np.abs(O.calcDe_planestress(E, nu)[np.ix_(ip, ip)] - O.calcDe(Es, nus)[np.ix_(ip, ip)]).max() < 1e-14 * E
+    assert np.abs(O.calcDe_planestress(E, nu)[2]).max() == 0.0
+
+
 # reference test/mech/elem/elastic-hex8.jl:10-75 (nodal, triangular face and volume load cases)
 @pytest.mark.parametrize("extra,uz", [
     (("z==1", NodeBC(fz=1)), [0, 0, 0, 0, 4.0, 4.0, 4.0, 4.0]),
