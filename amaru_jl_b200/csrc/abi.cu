@@ -78,10 +78,10 @@ void reset_status(amaru_model *m) { CUDA_CHECK(cudaMemsetAsync(m->d_status, 0, s
 
 amaru_model *amaru_create_impl(const CreateArgs &a) {
     AMARU_REQUIRE(a.ndim == 2 || a.ndim == 3, AMARU_ERR_ARG, "amaru_create: ndim must be 2 or 3");
-    AMARU_REQUIRE(a.stressmodel == AMARU_STRESS_D3 || a.stressmodel == AMARU_STRESS_PLANESTRAIN ||
-                      a.stressmodel == AMARU_STRESS_PLANESTRESS, AMARU_ERR_UNSUPPORTED,
-                  "amaru_create: only the d3 / planestrain / planestress stress models are on the B200 hot path (no CPU fallback)");
-    AMARU_REQUIRE(a.stressmodel != AMARU_STRESS_PLANESTRESS || a.ndim == 2, AMARU_ERR_ARG, "amaru_create: planestress needs ndim == 2");
+    AMARU_REQUIRE(a.stressmodel >= AMARU_STRESS_D3 && a.stressmodel <= AMARU_STRESS_AXISYMMETRIC, AMARU_ERR_UNSUPPORTED,
+                  "amaru_create: unknown stress model (d3, planestrain, planestress, axisymmetric)");
+    AMARU_REQUIRE((a.stressmodel != AMARU_STRESS_PLANESTRESS && a.stressmodel != AMARU_STRESS_AXISYMMETRIC) || a.ndim == 2,
+                  AMARU_ERR_ARG, "amaru_create: planestress / axisymmetric need ndim == 2");
     AMARU_REQUIRE(a.nnodes > 0 && a.nbatches > 0 && a.nmats > 0, AMARU_ERR_ARG, "amaru_create: empty model");
     AMARU_REQUIRE(a.coords && a.conn && a.elem_mat && a.mat_kind && a.mat_params && a.eqid && a.batch_shape &&
                       a.batch_nelem, AMARU_ERR_ARG, "amaru_create: null pointer");
@@ -872,6 +872,7 @@ int amaru_time_kernel(amaru_model *m, int kind, int precond, int reps, double *a
 
 int amaru_set_operator(amaru_model *m, int kind) {
     if (!m || (kind != AMARU_OPERATOR_CSR && kind != AMARU_OPERATOR_EBE)) return AMARU_ERR_ARG;
+    if (kind == AMARU_OPERATOR_EBE && m->stressmodel == AMARU_STRESS_AXISYMMETRIC) return AMARU_ERR_UNSUPPORTED;
     if (m->grp) return amaru_group_simple(m, 4, kind, 0, nullptr, 0);
     m->op_ebe = kind == AMARU_OPERATOR_EBE;
     return AMARU_OK;

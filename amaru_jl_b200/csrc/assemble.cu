@@ -184,7 +184,83 @@ __global__ void __launch_bounds__(NT) k_assemble_K(AsmArgs p) {
     }
 }
 
-// consistent mass: M_ab = Σ_ip ρ·detJ·w·th·N_a·N_b · I   (mech-solid.jl:169-205)
+
+// Axisymmetric tangent (stressmodel = :axisymmetric, 2D cells): B gets the hoop row ε_θθ = N_a/r (setB, mech-solid.jl:94-108)
+// and th = 2π·r of the integration point (:143).  One CTA per element, one thread per node pair, the four strain rows
+// (rr, zz, θθ, rz) written out; such models are small, so this kernel is plain rather than tuned.  Same colour-ordered
+// read-modify-write as k_assemble_K (no atomics, fixed order).
+template <int NN, int NIP>
+__global__ void __launch_bounds__(64) k_assemble_K_axi(AsmArgs p, const double *__restrict__ Nf) {
+    __shared__ double sX[NN * 2], sG[NIP][NN][2], sNr[NIP][NN], sD[NIP][16], sc[NIP];
+    const int tid = threadIdx.x;
+    const int64_t e = p.e_begin + blockIdx.x;
+    for (int i = tid; i < NN; i += 64) {
+        const int64_t node = p.conn[e * NN + i];
+        sX[i * 2] = p.coords[node * 3];
+        sX[i * 2 + 1] = p.coords[node * 3 + 1];
+    }
+    __syncthreads();
+    if (tid < NIP) {
+        const int q = tid;
+        double Ji[4];
+        const double det = am_jacobian<NN, 2>(sX, p.dNdR + q * NN * 2, Ji);
+        if (!(det > 0.0)) atomicMax(p.status, AMARU_FAIL_NEG_JACOBIAN);   // mech-solid.jl:150
+        double r = 0.0;
+        for (int a = 0; a < NN; a++) r += Nf[q * NN + a] * sX[a * 2];      // ip.coord.x
+        sc[q] = det * p.w[q] * 2.0 * 3.14159265358979323846 * r;
+        for (int a = 0; a < NN; a++) {
+            const double *dn = p.dNdR + (q * NN + a) * 2;
+            sG[q][a][0] = dn[0] * Ji[0] + dn[1] * Ji[2];
+            sG[q][a][1] = dn[0] * Ji[1] + dn[1] * Ji[3];
+            sNr[q][a] = Nf[q * NN + a] / r;
+        }
+        const int64_t ip = p.ip_off + e * NIP + q;
+        double sig[6];
+#pragma unroll
+        for (int c = 0; c < 6; c++) sig[c] = p.state[(int64_t)c * p.nip_total + ip];
+        const double dlam = p.state[(int64_t)13 * p.nip_total + ip];
+        const MatPar mp = load_mat(p.mat_kind, p.mat_par, p.emat[e]);
+        double D[36];
+        const int st = am_calcD(mp, sig, dlam, D);
+        if (st) atomicMax(p.status, st);
+        const int rows[4] = {0, 1, 2, 5};
+        for (int i = 0; i < 4; i++)
+            for (int j = 0; j < 4; j++) sD[q][i * 4 + j] = D[6 * rows[i] + rows[j]];
+    }
+    __syncthreads();
+    for (int ab = tid; ab < NN * NN; ab += 64) {
+        const int a = ab / NN, b = ab - a * NN;
+        double acc[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int q = 0; q < NIP; q++) {
+            // B_n (rows rr, zz, θθ, rz; columns u_r, u_z) = [g0 0; 0 g1; N/r 0; g1/√2 g0/√2]
+            const double Ba[4][2] = {{sG[q][a][0], 0.0}, {0.0, sG[q][a][1]}, {sNr[q][a], 0.0},
+                                     {sG[q][a][1] / AM_SR2, sG[q][a][0] / AM_SR2}};
+            const double Bb[4][2] = {{sG[q][b][0], 0.0}, {0.0, sG[q][b][1]}, {sNr[q][b], 0.0},
+                                     {sG[q][b][1] / AM_SR2, sG[q][b][0] / AM_SR2}};
+            double DB[4][2];
+            for (int i = 0; i < 4; i++)
+                for (int j = 0; j < 2; j++) {
+                    double v = 0.0;
+                    for (int k = 0; k < 4; k++) v += sD[q][i * 4 + k] * Bb[k][j];
+                    DB[i][j] = v;
+                }
+            for (int i = 0; i < 2; i++)
+                for (int j = 0; j < 2; j++) {
+                    double v = 0.0;
+                    for (int k = 0; k < 4; k++) v += Ba[k][i] * DB[k][j];
+                    acc[i * 2 + j] += sc[q] * v;
+                }
+        }
+        const int32_t dst = p.map[e * (int64_t)(NN * NN) + ab];
+        if (dst >= 0) {
+            double *Kb = p.K + (int64_t)dst * 4;
+#pragma unroll
+            for (int k = 0; k < 4; k++) Kb[k] += acc[k];
+        }
+    }
+}
+
+// consistent mass: M_ab = Σ_ip ρ·detJ·w·th·N_a·N_b · I   (mech-solid.jl:169-205; th = 2π·r when axisymmetric, :180)
 struct MassArgs {
     const double *coords;
     const int32_t *conn;
@@ -194,6 +270,7 @@ struct MassArgs {
     const double *N;
     const double *w;
     double th;
+    int axi;
     double *M;
     int *status;
     int64_t e_begin, e_end;
@@ -215,7 +292,13 @@ __global__ void __launch_bounds__(NT) k_assemble_M(MassArgs p) {
         double Ji[ND * ND];
         const double det = am_jacobian<NN, ND>(sX, p.dNdR + tid * NN * ND, Ji);
         if (!(det > 0.0)) atomicMax(p.status, AMARU_FAIL_NEG_JACOBIAN);
-        sc[tid] = p.rho[e] * det * p.w[tid] * p.th;
+        double th = p.th;
+        if (p.axi) {
+            double r = 0.0;
+            for (int a = 0; a < NN; a++) r += p.N[tid * NN + a] * sX[a * ND];
+            th = 2.0 * 3.14159265358979323846 * r;
+        }
+        sc[tid] = p.rho[e] * det * p.w[tid] * th;
     }
     __syncthreads();
     for (int ab = tid; ab < NN * NN; ab += NT) {
@@ -264,6 +347,25 @@ template <int NN, int ND, int NIP, int EPB, int NT>
 void launch_K(amaru_model *m, Batch &b) {
     using L = AsmSmem<NN, ND, NIP, EPB>;
     const size_t smem = L::doubles * sizeof(double);
+    if (m->stressmodel == AMARU_STRESS_AXISYMMETRIC) {
+        if constexpr (ND == 2) {
+            AsmArgs a;
+            a.coords = m->d_coords; a.conn = b.d_conn; a.emat = b.d_emat; a.map = b.d_map;
+            a.mat_kind = m->d_mat_kind; a.mat_par = m->d_mat_par; a.dNdR = b.d_dNdR; a.w = b.d_w;
+            a.state = m->d_state; a.nip_total = m->nip_total; a.ip_off = b.ip_off; a.th = m->th;
+            a.K = m->d_K; a.status = m->d_status;
+            for (size_t c = 0; c + 1 < b.color_off.size(); c++) {
+                a.e_begin = b.color_off[c];
+                a.e_end = b.color_off[c + 1];
+                const int64_t n = a.e_end - a.e_begin;
+                if (n <= 0) continue;
+                k_assemble_K_axi<NN, NIP><<<(unsigned)n, 64, 0, m->stream>>>(a, b.d_N);
+                m->launches++;
+            }
+            CUDA_CHECK(cudaGetLastError());
+        }
+        return;
+    }
     // function attributes are per device (multi-GPU handles drive several devices from one process): one bit per ordinal
     static std::atomic<uint64_t> attr_set{0};
     const uint64_t bit = 1ull << (m->device & 63);
@@ -293,7 +395,7 @@ template <int NN, int ND, int NIP>
 void launch_M(amaru_model *m, Batch &b) {
     MassArgs a;
     a.coords = m->d_coords; a.conn = b.d_conn; a.map = b.d_map; a.rho = b.d_rho; a.dNdR = b.d_dNdR; a.N = b.d_N;
-    a.w = b.d_w; a.th = m->th; a.M = m->d_M; a.status = m->d_status;
+    a.w = b.d_w; a.th = m->th; a.axi = m->stressmodel == AMARU_STRESS_AXISYMMETRIC; a.M = m->d_M; a.status = m->d_status;
     for (size_t c = 0; c + 1 < b.color_off.size(); c++) {
         a.e_begin = b.color_off[c];
         a.e_end = b.color_off[c + 1];

@@ -424,6 +424,7 @@ void amaru_ebe_setup(amaru_model *m) {
     // Tiny systems (BASELINE configs[0]: 200 QUAD8 elements) are pure latency: the colour-ordered kernel walks through its
     // colours one after the other (~4 us each with a handful of CTAs) while the block-CSR SpMV streams a few hundred KB in one
     // step; unless the environment says otherwise such handles start with the CSR operator (amaru_set_operator still switches).
+    if (m->stressmodel == AMARU_STRESS_AXISYMMETRIC) m->op_ebe = false;   // no hoop term in the matrix-free operator
     if (!op && m->nelem_total <= 1024 && 5e-6 + (double)m->nblk * m->nd * m->nd * 8.0 / 6.0e12 < 4e-6 * m->ncolors) m->op_ebe = false;
     Ebe *E = new Ebe();
     m->ebe = E;

@@ -242,6 +242,8 @@ int amaru_loadset_create(amaru_model *m, int shape, int64_t nents, const int32_t
         AMARU_REQUIRE(m && out, AMARU_ERR_ARG, "amaru_loadset_create: null argument");
         *out = nullptr;
         AMARU_REQUIRE(nents >= 0 && (nents == 0 || nodes), AMARU_ERR_ARG, "amaru_loadset_create: null node list");
+        AMARU_REQUIRE(m->stressmodel != AMARU_STRESS_AXISYMMETRIC, AMARU_ERR_UNSUPPORTED,
+                      "amaru_loadset_create: axisymmetric loads (th = 2*pi*r, distributed.jl:121,193) are integrated by the host glue");
         // a multi-GPU handle of one process integrates on its first GPU with the global arrays its wrapper keeps (group.cu)
         AMARU_REQUIRE(m->nranks == 1 || m->grp, AMARU_ERR_UNSUPPORTED,
                       "amaru_loadset_create: rank-level partitioned handles integrate loads per rank on the host");

@@ -32,6 +32,8 @@ struct UpdArgs {
     int *status;
     int64_t e_begin, e_end;
     int mode;          // 0 update_state!, 1 internal forces of the current stress
+    int axi;           // stressmodel = :axisymmetric (2D): hoop row of B, th = 2*pi*r (mech-solid.jl:94-108, 260-262)
+    const double *Nf;  // [NIP][NN] shape functions at the integration points (axisymmetric only)
 };
 
 template <int NN, int ND, int NIP, int NT>
@@ -59,7 +61,7 @@ __global__ void __launch_bounds__(NT) k_update(UpdArgs p) {
     __syncthreads();
     const int e = tid / NIP, q = tid - e * NIP;
     const bool active = e < ne;          // whole NIP-lane groups are active or not, so the shuffles below are safe
-    double Ji[ND * ND], coef = 0.0, ds[6];
+    double Ji[ND * ND], coef = 0.0, ds[6], rad = 1.0;
 #pragma unroll
     for (int c = 0; c < 6; c++) ds[c] = 0.0;
     if (active) {
@@ -68,6 +70,13 @@ __global__ void __launch_bounds__(NT) k_update(UpdArgs p) {
         // no detJ > 0 test here: the reference's update_elem! has none (mech-solid.jl:243-279; only elem_stiffness :150 and
         // elem_mass :194 raise), and with fixed coordinates the assembly that precedes every update has already tested it
         coef = det * sw[q] * p.th;
+        if constexpr (ND == 2) {
+            if (p.axi) {
+                rad = 0.0;
+                for (int a = 0; a < NN; a++) rad += p.Nf[q * NN + a] * X[a * 2];   // ip.coord.x
+                coef = det * sw[q] * 2.0 * 3.14159265358979323846 * rad;
+            }
+        }
         const int64_t ip = p.ip_off + (e0 + e) * NIP + q;
         if (p.mode == 0) {
             double de[6];
@@ -95,6 +104,7 @@ __global__ void __launch_bounds__(NT) k_update(UpdArgs p) {
                     const double ux = U[a * 2], uy = U[a * 2 + 1];
                     de[0] += g[0] * ux;
                     de[1] += g[1] * uy;
+                    if (p.axi) de[2] += (p.Nf[q * NN + a] / rad) * ux;
                     de[5] += (g[1] / AM_SR2) * ux + (g[0] / AM_SR2) * uy;
                 }
             }
@@ -141,6 +151,7 @@ __global__ void __launch_bounds__(NT) k_update(UpdArgs p) {
                 f[2] = coef * (g[2] * ds[2] + hy * ds[3] + hx * ds[4]);
             } else {
                 f[0] = coef * (g[0] * ds[0] + (g[1] / AM_SR2) * ds[5]);
+                if (p.axi && active) f[0] += coef * (p.Nf[q * NN + a] / rad) * ds[2];
                 f[1] = coef * (g[1] * ds[1] + (g[0] / AM_SR2) * ds[5]);
             }
         }
@@ -165,6 +176,7 @@ void launch_upd(amaru_model *m, Batch &b, const double *dU, double *f, int mode)
     a.mat_kind = m->d_mat_kind; a.mat_par = m->d_mat_par; a.dNdR = b.d_dNdR; a.w = b.d_w;
     a.state = m->d_state; a.nip_total = m->nip_total; a.ip_off = b.ip_off; a.th = m->th;
     a.dU = dU; a.f = f; a.status = m->d_status; a.mode = mode;
+    a.axi = m->stressmodel == AMARU_STRESS_AXISYMMETRIC; a.Nf = b.d_N;
     constexpr int EPB = NT / NIP;
     for (size_t c = 0; c + 1 < b.color_off.size(); c++) {
         a.e_begin = b.color_off[c];

@@ -154,8 +154,8 @@ class FEModel:
         ctx.ndim = mesh.ndim                                         # fe-model.jl:94
         if ctx.ndim == 3 and ctx.stressmodel not in ("d3", "none"):
             raise AmaruError("FEModel: 3D models need stressmodel d3")
-        if ctx.stressmodel == "axisymmetric":
-            raise AmaruError(f"stressmodel {ctx.stressmodel} is outside the B200 hot path (no CPU fallback)")
+        if ctx.stressmodel == "axisymmetric" and ctx.ndim != 2:
+            raise AmaruError("FEModel: axisymmetric models are 2D")
         self.thickness = float(thickness)
         self.ndim = ctx.ndim
         self.shape = mesh.shape
@@ -282,6 +282,8 @@ class FEModel:
         U = np.zeros(ndofs)
         F = np.zeros(ndofs)
         X = self.coords
+        if self.ctx.stressmodel == "axisymmetric":
+            device = None          # th = 2*pi*r per integration point: integrated by the numpy path (loads.cu refuses it)
         for bc, target in setup:
             if isinstance(bc, NodeBC):                                # bc.jl:43-58
                 nodes = target
@@ -368,7 +370,8 @@ class FEModel:
                 Q = vip[:, None] * nrm / np.sqrt((nrm ** 2).sum(axis=1))[:, None]
             else:
                 Q[:, ("tx", "ty", "tz").index(key)] = vip
-            coef = nJ * q[3] * th
+            tq = 2 * np.pi * x if self.ctx.stressmodel == "axisymmetric" else th      # distributed.jl:121
+            coef = nJ * q[3] * tq
             Fd += coef[:, None, None] * N[None, :, None] * Q[:, None, :]
         return Fd
 
@@ -390,7 +393,8 @@ class FEModel:
             vip = np.broadcast_to(evaluate(val, x=x, y=y, z=z), x.shape)
             Q = np.zeros((C.shape[0], nd))
             Q[:, ("wx", "wy", "wz").index(key)] = vip
-            coef = np.linalg.det(J) * q[3] * self.thickness
+            tq = 2 * np.pi * x if self.ctx.stressmodel == "axisymmetric" else self.thickness   # distributed.jl:193
+            coef = np.linalg.det(J) * q[3] * tq
             Fd += coef[:, None, None] * N[None, :, None] * Q[:, None, :]
         return Fd
 
@@ -398,7 +402,7 @@ class FEModel:
     def flatten(self):
         """Arrays exactly as amaru_create takes them (include/amaru_b200.h)."""
         return dict(
-            ndim=self.ndim, stressmodel={"d3": 0, "none": 0, "planestrain": 1, "planestress": 2}[self.ctx.stressmodel],
+            ndim=self.ndim, stressmodel={"d3": 0, "none": 0, "planestrain": 1, "planestress": 2, "axisymmetric": 3}[self.ctx.stressmodel],
             thickness=self.thickness, coords=np.ascontiguousarray(self.coords, dtype=np.float64),
             batch_shape=np.array([self.shape.id], dtype=np.int32),
             batch_nelem=np.array([self.nelems], dtype=np.int64),

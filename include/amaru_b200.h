@@ -65,6 +65,10 @@ extern "C" {
 /* plane stress, LinearElastic only (the only material whose calcDe has that branch, linear-elastic.jl:99-108): 2D models;
  * σzz stays zero, the in-plane moduli are c = E/(1-ν²): c, cν, c(1-ν) */
 #define AMARU_STRESS_PLANESTRESS 2
+/* axisymmetric (2D cells in the r-z plane): hoop row ε_θθ = N_a/r of B and th = 2π·r at every integration point
+ * (mech-solid.jl:94-108,143,180,260); the PCG of such handles runs on the assembled block-CSR matrix (the matrix-free
+ * operator has no hoop term) and distributed loads are integrated by the host glue (distributed.jl:121,193) */
+#define AMARU_STRESS_AXISYMMETRIC 3
 
 /* preconditioners for the PCG that replaces lu(K11) (solver.jl:42-43) */
 #define AMARU_PRECOND_JACOBI 0

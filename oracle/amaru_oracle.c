@@ -442,13 +442,27 @@ static double jacobian(int nn, int nd, const double *C, const double *dNdR, doub
     return det;
 }
 
-/* setB (mech-solid.jl:82-121), non-axisymmetric.  B is 6 x ne row-major, pre-zeroed. */
-static void setB(int nn, int nd, const double *dNdX, double *B) {
+/* stressmodel = :axisymmetric (mech-solver.jl:9): the element routines below read this switch, set per model by
+ * orc_set_axisymmetric (the python wrapper sets it before every call into this file). */
+static int g_axi = 0;
+void orc_set_axisymmetric(int on) { g_axi = on; }
+
+/* ip.coord.x = (C'N)[1]: the radius of the integration point (ip coordinates are set from the shape functions, fe-model.jl) */
+static double ip_radius(int nn, int nd, const double *C, const double *N) {
+    double r = 0;
+    for (int a = 0; a < nn; a++) r += N[a] * C[nd * a];
+    return r;
+}
+
+/* setB (mech-solid.jl:82-121).  B is 6 x ne row-major, pre-zeroed.  N, r: shape functions and radius of the integration
+ * point, used by the axisymmetric branch only (:94-108: hoop strain N_i/r in row 3). */
+static void setB(int nn, int nd, const double *dNdX, double *B, const double *N, double r) {
     const int ne = nn * nd;
     if (nd == 2) {
         for (int i = 0; i < nn; i++) {
             B[0 * ne + 0 + i * 2] = dNdX[2 * i + 0];
             B[1 * ne + 1 + i * 2] = dNdX[2 * i + 1];
+            if (g_axi) B[2 * ne + 0 + i * 2] = N[i] / r;
             B[5 * ne + 0 + i * 2] = dNdX[2 * i + 1] / SR2;
             B[5 * ne + 1 + i * 2] = dNdX[2 * i + 0] / SR2;
         }
@@ -471,15 +485,18 @@ static void setB(int nn, int nd, const double *dNdX, double *B) {
 int orc_elem_stiffness(int shape, double th, const double *C, int kind, const double *par, const double *sig,
                        const double *dlam, double *K) {
     const int nn = orc_shape_nn(shape), nd = orc_shape_ndim(shape), ne = nn * nd;
-    double ips[8 * 4], dNdR[MAXNN * 3], dNdX[MAXNN * 3], B[6 * MAXNE], DB[6 * MAXNE], D[36];
+    double ips[8 * 4], dNdR[MAXNN * 3], dNdX[MAXNN * 3], B[6 * MAXNE], DB[6 * MAXNE], D[36], N[MAXNN];
     const int nip = orc_quadrature(shape, ips);
     memset(K, 0, sizeof(double) * ne * ne);
     memset(B, 0, sizeof B);
     for (int q = 0; q < nip; q++) {
+        orc_shape_func(shape, &ips[4 * q], N);
+        const double r = ip_radius(nn, nd, C, N);
+        if (g_axi) th = 2.0 * M_PI * r;                                /* mech-solid.jl:143 */
         orc_shape_deriv(shape, &ips[4 * q], dNdR);
         const double detJ = jacobian(nn, nd, C, dNdR, dNdX);
         if (!(detJ > 0.0)) return 4;
-        setB(nn, nd, dNdX, B);
+        setB(nn, nd, dNdX, B, N, r);
         const double coef = detJ * ips[4 * q + 3] * th;
         const int st = orc_calcD(kind, par, &sig[6 * q], dlam[q], D);
         if (st) return st;
@@ -507,6 +524,7 @@ int orc_elem_mass(int shape, double th, double rho, const double *C, double *M) 
     memset(M, 0, sizeof(double) * ne * ne);
     for (int q = 0; q < nip; q++) {
         orc_shape_func(shape, &ips[4 * q], N);
+        if (g_axi) th = 2.0 * M_PI * ip_radius(nn, nd, C, N);          /* mech-solid.jl:180 */
         orc_shape_deriv(shape, &ips[4 * q], dNdR);
         const double detJ = jacobian(nn, nd, C, dNdR, dNdX);
         if (!(detJ > 0.0)) return 4;
@@ -523,14 +541,17 @@ int orc_elem_mass(int shape, double th, double rho, const double *C, double *M) 
 int orc_update_elem(int shape, double th, const double *C, int kind, const double *par, double *sig,
                     double *eps, double *epa, double *dlam, const double *dU, double *dF) {
     const int nn = orc_shape_nn(shape), nd = orc_shape_ndim(shape), ne = nn * nd;
-    double ips[8 * 4], dNdR[MAXNN * 3], dNdX[MAXNN * 3], B[6 * MAXNE];
+    double ips[8 * 4], dNdR[MAXNN * 3], dNdX[MAXNN * 3], B[6 * MAXNE], N[MAXNN];
     const int nip = orc_quadrature(shape, ips);
     memset(dF, 0, sizeof(double) * ne);
     memset(B, 0, sizeof B);
     for (int q = 0; q < nip; q++) {
+        orc_shape_func(shape, &ips[4 * q], N);
+        const double r = ip_radius(nn, nd, C, N);
+        if (g_axi) th = 2.0 * M_PI * r;                                /* mech-solid.jl:260-262 */
         orc_shape_deriv(shape, &ips[4 * q], dNdR);
         const double detJ = jacobian(nn, nd, C, dNdR, dNdX);
-        setB(nn, nd, dNdX, B);
+        setB(nn, nd, dNdX, B, N, r);
         double de[6], ds[6];
         for (int i = 0; i < 6; i++) {
             double v = 0;
@@ -552,14 +573,17 @@ int orc_update_elem(int shape, double th, const double *C, int kind, const doubl
 /* elem_internal_forces (mech-solid.jl:208-240): dF = Σ coef B'σ */
 int orc_elem_internal_forces(int shape, double th, const double *C, const double *sig, double *dF) {
     const int nn = orc_shape_nn(shape), nd = orc_shape_ndim(shape), ne = nn * nd;
-    double ips[8 * 4], dNdR[MAXNN * 3], dNdX[MAXNN * 3], B[6 * MAXNE];
+    double ips[8 * 4], dNdR[MAXNN * 3], dNdX[MAXNN * 3], B[6 * MAXNE], N[MAXNN];
     const int nip = orc_quadrature(shape, ips);
     memset(dF, 0, sizeof(double) * ne);
     memset(B, 0, sizeof B);
     for (int q = 0; q < nip; q++) {
+        orc_shape_func(shape, &ips[4 * q], N);
+        const double r = ip_radius(nn, nd, C, N);
+        if (g_axi) th = 2.0 * M_PI * r;                                /* mech-solid.jl:222-224 */
         orc_shape_deriv(shape, &ips[4 * q], dNdR);
         const double detJ = jacobian(nn, nd, C, dNdR, dNdX);
-        setB(nn, nd, dNdX, B);
+        setB(nn, nd, dNdX, B, N, r);
         const double coef = detJ * ips[4 * q + 3] * th;
         for (int j = 0; j < ne; j++) {
             double v = 0;

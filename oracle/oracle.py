@@ -164,6 +164,7 @@ class OracleModel:
             assert (self.mat_kind == 1).all(), "planestress: LinearElastic only"
             self.mat_kind[:] = 4
         self.mat_par = np.ascontiguousarray(flat["mat_params"], dtype=np.float64)
+        self.axi = int(flat.get("stressmodel", 0)) == 3   # :axisymmetric (hoop row of B, th = 2*pi*r; mech-solid.jl:94-108,143)
         self.eqid = np.ascontiguousarray(eqid, dtype=np.int32)
         self.ndofs, self.nu = int(ndofs), int(nu)
         self.nn = lib().orc_shape_nn(self.shape)
@@ -192,6 +193,7 @@ class OracleModel:
         vals = np.empty(nt, dtype=np.float64)
         ntrip = C.c_int64(0)
         rho = np.zeros(self.nelem) if rho is None else np.ascontiguousarray(rho, dtype=np.float64)
+        lib().orc_set_axisymmetric(int(self.axi))
         st = lib().orc_mount_coo(mode, self.shape, C.c_double(self.th), C.c_int64(self.nelem), _d(self.coords),
                                  _i(self.conn), _i(self.elem_mat), _i(self.mat_kind), _d(self.mat_par), _d(rho),
                                  _i(self.eqid), _d(self.sig), _d(self.dlam), int(filter_eps), _l(rows), _l(cols),
@@ -229,6 +231,7 @@ class OracleModel:
         """update_state! (mech-solver.jl:124-144) -> (dFin, status)."""
         dU = np.ascontiguousarray(dU, dtype=np.float64)
         dF = np.zeros(self.ndofs)
+        lib().orc_set_axisymmetric(int(self.axi))
         st = lib().orc_update_state(self.shape, C.c_double(self.th), C.c_int64(self.nelem), _d(self.coords),
                                     _i(self.conn), _i(self.elem_mat), _i(self.mat_kind), _d(self.mat_par),
                                     _i(self.eqid), C.c_int64(self.ndofs), _d(self.sig), _d(self.eps), _d(self.epa),
@@ -237,6 +240,7 @@ class OracleModel:
 
     def internal_forces(self):
         F = np.zeros(self.ndofs)
+        lib().orc_set_axisymmetric(int(self.axi))
         lib().orc_internal_forces(self.shape, C.c_double(self.th), C.c_int64(self.nelem), _d(self.coords),
                                   _i(self.conn), _i(self.eqid), C.c_int64(self.ndofs), _d(self.sig), _d(F))
         return F

@@ -92,7 +92,7 @@ def ip_coords(shape, coords, nodes, ndim):
     return X
 
 
-def entity_forces(shape, C, ndim, th, key, vals):
+def entity_forces(shape, C, ndim, th, key, vals, axi=False):
     """One call of mech_boundary_forces (facet) / mech_solid_body_forces (cell): C (nn, ndim), vals (nip,) -> (nn, ndim)."""
     ips = quadrature(shape)
     facet = shape_dim(shape) < ndim        # faces, 2D edges, and the 3D edges of EdgeBC (qx qy qz; th = 1.0, distributed.jl:95)
@@ -109,17 +109,19 @@ def entity_forces(shape, C, ndim, th, key, vals):
             Q = vals[q] * n / np.sqrt((n * n).sum())
         else:
             Q[key] = vals[q]
+        if axi:
+            th = 2 * np.pi * float(C[:, 0] @ N)      # ctx.stressmodel==:axisymmetric && (th = 2*pi*X[1]), distributed.jl:121,193
         coef = (norm2(J) if facet else float(np.linalg.det(J))) * w * th
         F += coef * np.outer(N, Q)
     return F
 
 
-def apply(shape, coords, nodes, eqid, ndim, th, key, vals, F):
+def apply(shape, coords, nodes, eqid, ndim, th, key, vals, F, axi=False):
     """F[map] += Fd for every entity in order (bc.jl:131-134,189-192). vals: scalar or (nents*nip,)."""
     nip = quadrature(shape).shape[0]
     vals = np.broadcast_to(np.asarray(vals, dtype=np.float64), (nodes.shape[0] * nip,)) if np.ndim(vals) == 0 else vals
     for e in range(nodes.shape[0]):
-        Fd = entity_forces(shape, coords[nodes[e], :ndim], ndim, th, key, vals[e * nip:(e + 1) * nip])
+        Fd = entity_forces(shape, coords[nodes[e], :ndim], ndim, th, key, vals[e * nip:(e + 1) * nip], axi)
         emap = eqid[nodes[e]].reshape(-1)
         F[emap] += Fd.reshape(-1)      # node-major map, no repeated node inside one entity
     return F

@@ -45,8 +45,9 @@ def test_no_cpu_fallback_without_device():
 def test_unsupported_features_are_refused_on_the_host():
     from amaru_jl_b200 import AmaruError, Block, FEModel, LinearElastic, MechContext, MechSolid, Mesh
     mesh = Mesh(Block([[0, 0], [1, 1]], nx=1, ny=1, cellshape="QUAD8", tag="s"))
-    with pytest.raises(AmaruError):
-        FEModel(mesh, [("s", MechSolid, LinearElastic, dict(E=1.0, nu=0.3))], MechContext(stressmodel="axisymmetric"))
+    mesh3 = Mesh(Block([[0, 0, 0], [1, 1, 1]], nx=1, ny=1, nz=1, cellshape="HEX8", tag="s"))
+    with pytest.raises(AmaruError):                      # axisymmetric / plane models are 2D
+        FEModel(mesh3, [("s", MechSolid, LinearElastic, dict(E=1.0, nu=0.3))], MechContext(stressmodel="axisymmetric"))
     from amaru_jl_b200 import VonMises
     with pytest.raises(AmaruError):                      # plane stress: LinearElastic only (linear-elastic.jl:99-108)
         FEModel(mesh, [("s", MechSolid, VonMises, dict(E=1.0, nu=0.3, fy=1.0))], MechContext(stressmodel="planestress"))

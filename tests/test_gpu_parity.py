@@ -507,3 +507,55 @@ def test_plane_stress_linear_elastic(shape, n, op):
     assert rel(s["sigma"], om.sig) < 1e-12 and np.abs(s["sigma"][:, 2]).max() == 0.0
     assert rel(s["eps"], om.eps) < 1e-12
     dm.close()
+
+
+@pytest.mark.parametrize("shape,n", [("QUAD4", 5), ("QUAD8", 4)])
+@pytest.mark.parametrize("mat", ["le", "vm", "dp"])
+def test_axisymmetric(shape, n, mat):
+    """stressmodel = :axisymmetric (AMARU_STRESS_AXISYMMETRIC): hoop row N_a/r of B and th = 2*pi*r in mount_K, update_state!,
+    elem_internal_forces and mount_M (mech-solid.jl:94-108,143,180,222,260) against the oracle (pinned to the Lamé cylinder in
+    tests/test_oracle_golden.py): pattern bit-exact, K / f_int / IP state 1e-12, u 1e-8 over two chained plastic steps; the
+    PCG of such handles runs on the block-CSR matrix (the matrix-free operator is refused)."""
+    mesh = Mesh(Block([[1.0, 0], [3.0, 1.0]], nx=2 * n, ny=n, cellshape=shape, tag="solids"))
+    rng = np.random.default_rng(7)
+    c = mesh.coords
+    interior = (c[:, 0] > 1 + 1e-9) & (c[:, 0] < 3 - 1e-9) & (c[:, 1] > 1e-9) & (c[:, 1] < 1 - 1e-9)
+    c[interior, :2] += rng.uniform(-0.15, 0.15, (interior.sum(), 2)) / (2 * n + 2)
+    mesh.coords[...] = np.round(c, 8)
+    mty, par = MATS[mat]
+    model = FEModel(mesh, [("solids", MechSolid, mty, par)], MechContext(stressmodel="axisymmetric"))
+    bcs = [("y==0", NodeBC(uy=0)), ("x==1", NodeBC(ux=0.002 if mat != "dp" else 0.004)), ("y==1", SurfaceBC(ty="-0.1*x")),
+           ("x>=0", BodyC(wy=-0.05))]
+    om, dm, eqid, nu, setup = pair(model, bcs)
+    assert "spmv" in dm.spmv_kernel
+    with pytest.raises(L.AmaruStatus):
+        dm.set_operator("ebe")
+    Uex, Fex = model.get_bc_vals(eqid, setup, device=dm)              # axisymmetric loads: host path (th = 2*pi*r)
+    import oracle.oracle_loads as OL
+    fn, _ = [t for b, t in setup if isinstance(b, SurfaceBC)][0]
+    Fo = np.zeros(eqid.size)
+    ipx = OL.ip_coords(model.shape.facet_shape.id, model.coords, fn, 2)
+    OL.apply(model.shape.facet_shape.id, model.coords, fn, eqid, 2, 1.0, 1, -0.1 * ipx[:, 0], Fo, axi=True)
+    OL.apply(model.shape.id, model.coords, model.conn, eqid, 2, 1.0, 1, -0.05, Fo, axi=True)
+    assert rel(Fex, Fo) < 1e-12
+    for it in range(2):
+        K = check_K(om, dm)
+        U, F = Uex.copy(), Fex.copy()
+        dm.solve(U, F, cg_rtol=1e-12)
+        Uo, Fo2 = Uex.copy(), Fex.copy()
+        ok, _ = O.solve_system(K, Uo, Fo2, nu)
+        assert ok and rel(U, Uo) < 1e-8 and rel(F[nu:], Fo2[nu:]) < 1e-8
+        dF = dm.update_state((1.0 + it) * Uo)
+        dFo, st = om.update_state((1.0 + it) * Uo)
+        assert st == 0 and rel(dF, dFo) < 1e-12
+        s = dm.get_state()
+        assert rel(s["sigma"], om.sig) < 1e-12 and rel(s["eps"], om.eps) < 1e-12 and rel(s["epa"], om.epa) < 1e-11
+        assert rel(dm.internal_forces(), om.internal_forces()) < 1e-12
+    if mat != "le":
+        assert (om.dlam > 0).sum() > 0
+    rho = rng.uniform(1.0, 3.0, model.nelems)
+    dm.assemble_M(rho)
+    _, M = om.mount_M(rho, filter_eps=False)
+    x = rng.uniform(-1, 1, eqid.size)
+    assert rel(dm.matvec(0.0, 1.0, x), M.tocsr() @ x) < 1e-12
+    dm.close()

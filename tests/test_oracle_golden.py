@@ -96,6 +96,26 @@ def test_elastic_quad4_planestress():
     assert np.abs(O.calcDe_planestress(E, nu)[2]).max() == 0.0
 
 
+def test_axisymmetric_lame_cylinder():
+    """stressmodel = :axisymmetric (hoop row of B, th = 2*pi*r: mech-solid.jl:94-108,143; distributed.jl:121) against the Lamé
+    solution of a thick-walled cylinder (a = 1, b = 2) under internal pressure with plane-strain ends:
+    u_r = p a² (1+ν) / (E (b²-a²)) · ((1-2ν) r + b²/r); σ_θθ(a) = p (a²+b²)/(b²-a²)."""
+    E, nu, p, a, b = 1000.0, 0.3, 1.0, 1.0, 2.0
+    mesh = Mesh(Block([[a, 0], [b, 0.2]], nx=24, ny=1, cellshape="QUAD8", tag="solid"))
+    model = FEModel(mesh, [("solid", MechSolid, LinearElastic, dict(E=E, nu=nu))], MechContext(stressmodel="axisymmetric"))
+    bcs = [("y==0", NodeBC(uy=0)), ("y==0.2", NodeBC(uy=0)), (f"x=={a}", SurfaceBC(tx=p))]
+    res, eqid, om = run(model, bcs, nincs=1)
+    assert res["success"]
+    U = res["U"][eqid]
+    r = model.coords[:, 0]
+    ur = p * a * a * (1 + nu) / (E * (b * b - a * a)) * ((1 - 2 * nu) * r + b * b / r)
+    assert np.abs(U[:, 0] - ur).max() < 2e-6 * np.abs(ur).max() and np.abs(U[:, 1]).max() < 1e-12
+    # hoop stress at the integration points (Mandel component 3 = θθ): Lamé σ_θθ = p a²/(b²-a²) (1 + b²/r²)
+    ipr = model.ip_coords()[:, 0]
+    sth = p * a * a / (b * b - a * a) * (1 + b * b / ipr ** 2)
+    assert np.abs(om.sig[:, 2] - sth).max() < 2e-4 * sth.max()
+
+
 # reference test/mech/elem/elastic-hex8.jl:10-75 (nodal, triangular face and volume load cases)
 @pytest.mark.parametrize("extra,uz", [
     (("z==1", NodeBC(fz=1)), [0, 0, 0, 0, 4.0, 4.0, 4.0, 4.0]),
