@@ -143,10 +143,17 @@ __global__ void __launch_bounds__(NT) k_assemble_K(AsmArgs p) {
     }
     __syncthreads();
 
-    // one thread per (element, a, b): nd x nd block
-    for (int i = tid; i < ne * NN * NN; i += NT) {
-        const int e = i / (NN * NN), ab = i - e * NN * NN;
-        const int a = ab / NN, b = ab - a * NN;
+    // one thread per (element, a <= b): nd x nd block K_ab; the tangent of all three materials is symmetric (associated flow),
+    // so K_ba = K_abᵀ is written from the same registers — half the contractions of the round-1 kernel
+    constexpr int NPAIR = NN * (NN + 1) / 2;
+    for (int i = tid; i < ne * NPAIR; i += NT) {
+        const int e = i / NPAIR, t = i - e * NPAIR;
+        int a = 0, rem = t;                              // t -> (a, b), rows of the upper triangle
+        while (rem >= NN - a) {
+            rem -= NN - a;
+            a++;
+        }
+        const int b = a + rem, ab = a * NN + b;
         double acc[BS2];
 #pragma unroll
         for (int k = 0; k < BS2; k++) acc[k] = 0.0;
@@ -180,6 +187,16 @@ __global__ void __launch_bounds__(NT) k_assemble_K(AsmArgs p) {
             double *Kb = p.K + (int64_t)dst * BS2;
 #pragma unroll
             for (int k = 0; k < BS2; k++) Kb[k] += acc[k];
+        }
+        if (a != b) {
+            const int32_t dst2 = p.map[(e0 + e) * (int64_t)(NN * NN) + b * NN + a];
+            if (dst2 >= 0) {
+                double *Kb = p.K + (int64_t)dst2 * BS2;
+#pragma unroll
+                for (int r = 0; r < ND; r++)
+#pragma unroll
+                    for (int c = 0; c < ND; c++) Kb[r * ND + c] += acc[c * ND + r];
+            }
         }
     }
 }
