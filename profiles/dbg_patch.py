@@ -3,7 +3,7 @@ import faulthandler
 import os
 import sys
 
-faulthandler.dump_traceback_later(25, exit=True)
+faulthandler.dump_traceback_later(280, exit=True)
 os.environ.setdefault("AMARU_EBE_PATCH_MINFILL", "0")
 os.environ.setdefault("AMARU_EBE_PATCH_MINPATCH", "0")
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
