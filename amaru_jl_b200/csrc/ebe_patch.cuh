@@ -66,7 +66,8 @@ struct PatchLayout {
     static constexpr int WARPS = 4;
     static constexpr int NID = M::KS2 + 2 * M::NT3;              // patch-local ids per lane and group
     static constexpr int NW = (NID + 3) / 4;                     // 64-bit words of packed ids per lane and group
-    static constexpr size_t warp_bytes = (size_t)MAXPN * ND * 8 * 2 + (size_t)MAXPN * 4;
+    // x and y bricks hold MAXPN rows + one dummy row (zero; never written) that padded fragment positions and empty slots address
+    static constexpr size_t warp_bytes = (size_t)(MAXPN + 1) * ND * 8 * 2 + (size_t)MAXPN * 4;
     static constexpr size_t bytes = M::tab_doubles * 8 + 3 * EBE_SMATS * 8 + WARPS * warp_bytes;
 };
 
@@ -82,9 +83,10 @@ __global__ void __launch_bounds__(128, 2) k_ebe_patch(PatchArgs p) {
     double *sDog = sB3 + KS3 * NT3 * 32;                 // [EBE_SMATS][3]
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     char *wbase = reinterpret_cast<char *>(sDog + 3 * EBE_SMATS) + (size_t)wid * L::warp_bytes;
-    double *sX = reinterpret_cast<double *>(wbase);      // [MAXPN][ND]
-    double *sY = sX + MAXPN * ND;                        // [MAXPN][ND]
-    uint32_t *sP = reinterpret_cast<uint32_t *>(sY + MAXPN * ND);   // [MAXPN] node entries
+    double *sX = reinterpret_cast<double *>(wbase);      // [MAXPN + 1][ND]
+    double *sY = sX + (MAXPN + 1) * ND;                  // [MAXPN + 1][ND]
+    uint32_t *sP = reinterpret_cast<uint32_t *>(sY + (MAXPN + 1) * ND);   // [MAXPN] node entries
+    if (lane < ND) sX[MAXPN * ND + lane] = sY[MAXPN * ND + lane] = 0.0;   // the dummy row
     const int er = lane >> 2, j = lane & 3;
     __shared__ int s_last;
 
@@ -281,7 +283,7 @@ __global__ void __launch_bounds__(128, 2) k_ebe_patch(PatchArgs p) {
                 for (int n = 0; n < NT2; n++) b[n] = sB2[(s * NT2 + n) * 32 + lane];
                 // no lane-dependent condition here: mma.sync needs every lane, and a select on `act` invites the compiler to
                 // branch around the loads with the DMMAs inside (observed: the 2D instantiations hung).  Empty slots and
-                // padded node columns carry local id 0 (a valid, finite x entry) and meet zero rows of B2 / zero J⁻¹, coef.
+                // padded node columns carry the id of the dummy row behind the brick (zero, never written).
 #pragma unroll
                 for (int i = 0; i < ND; i++) {
                     const double a = sX[l1[s] * ND + i];

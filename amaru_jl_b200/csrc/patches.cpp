@@ -215,7 +215,7 @@ void amaru_build_patches(int nn, int nd, int pe, int maxpn, const int brick[3], 
             size_t k1 = k;
             while (k1 < ce.size() && ce[k1].first == ce[k].first && k1 - k < 8) k1++;
             const size_t g0 = out.lane_ids.size();
-            out.lane_ids.resize(g0 + (size_t)nw * 128, 0);
+            out.lane_ids.resize(g0 + (size_t)nw * 128, (uint16_t)maxpn);   // padding / empty slots: the dummy row behind the brick
             for (size_t s = 0; s < 8; s++) {
                 const int32_t e = k + s < k1 ? ce[k + s].second : -1;
                 out.slot_elem.push_back(e);
