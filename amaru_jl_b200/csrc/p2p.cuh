@@ -82,19 +82,25 @@ __device__ __forceinline__ void p2p_push_scalars(const P2PDev &pd, unsigned long
         st_release_sys(&w->sflag[par][pd.rank], epoch);
     }
 }
-// first warp of a CTA (all 32 lanes): lane r waits for rank r's flag (the waits overlap), then every lane forms the sum
-// over the ranks in rank order; out[0..n) valid in every lane; false on time-out / abort
+// first warp of a CTA (all 32 lanes): lane r waits for rank r's flag (the waits overlap) and reads rank r's slot itself — the
+// lane that acquired the flag is the one that reads the data behind it —, then the values are summed in rank order through
+// shuffles; out[0..n) valid in every lane; false on time-out / abort
 __device__ __forceinline__ bool p2p_collect(const P2PDev &pd, unsigned long long epoch, double *out, int n) {
     P2PWin *me = pd.win[pd.rank];
     const int par = (int)(epoch & 1ull);
     const int lane = threadIdx.x & 31;
     bool ok = true;
-    if (lane < pd.nranks) ok = p2p_wait(pd, &me->sflag[par][lane], epoch);
+    double mine[4] = {0.0, 0.0, 0.0, 0.0};
+    if (lane < pd.nranks) {
+        ok = p2p_wait(pd, &me->sflag[par][lane], epoch);
+        if (ok)
+            for (int k = 0; k < n; k++) mine[k] = *reinterpret_cast<volatile double *>(&me->slot[par][lane][k]);
+    }
     ok = __all_sync(0xffffffffu, ok);
     if (!ok) return false;
     for (int k = 0; k < n; k++) {
-        double s = *reinterpret_cast<volatile double *>(&me->slot[par][0][k]);
-        for (int r = 1; r < pd.nranks; r++) s += *reinterpret_cast<volatile double *>(&me->slot[par][r][k]);
+        double s = __shfl_sync(0xffffffffu, mine[k], 0);
+        for (int r = 1; r < pd.nranks; r++) s += __shfl_sync(0xffffffffu, mine[k], r);
         out[k] = s;
     }
     return true;
