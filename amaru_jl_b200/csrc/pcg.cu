@@ -27,17 +27,23 @@ namespace {
 constexpr int CG_BATCH = 20;
 constexpr int ROW_THREADS = 256;
 
-// z = M⁻¹ r for one node
+// z = M⁻¹ r for one node.  Block-Jacobi: the inverse of the (symmetric) diagonal block is stored as its upper triangle,
+// BS(BS+1)/2 doubles per node in row order (00 01 02 11 12 22): 48 instead of 72 bytes per node in every CG iteration.
 template <int BS, bool BLOCKJ>
 __device__ __forceinline__ void apply_minv(const double *__restrict__ Minv, int64_t node, const double *r, double *z) {
     if (BLOCKJ) {
-        const double *M = Minv + node * BS * BS;
+        constexpr int NS = BS * (BS + 1) / 2;
+        const double *M = Minv + node * NS;
+        double m[NS];
 #pragma unroll
-        for (int i = 0; i < BS; i++) {
-            double s = 0.0;
-#pragma unroll
-            for (int j = 0; j < BS; j++) s += M[i * BS + j] * r[j];
-            z[i] = s;
+        for (int k = 0; k < NS; k++) m[k] = M[k];
+        if constexpr (BS == 3) {
+            z[0] = m[0] * r[0] + m[1] * r[1] + m[2] * r[2];
+            z[1] = m[1] * r[0] + m[3] * r[1] + m[4] * r[2];
+            z[2] = m[2] * r[0] + m[4] * r[1] + m[5] * r[2];
+        } else {
+            z[0] = m[0] * r[0] + m[1] * r[1];
+            z[1] = m[1] * r[0] + m[2] * r[1];
         }
     } else {
 #pragma unroll
@@ -316,16 +322,20 @@ __global__ void k_block_inverse(int64_t nnodes, const int32_t *__restrict__ diag
 #pragma unroll
             for (int i = 0; i < BS; i++) Minv[n * BS + i] = 1.0 / D[i * BS + i];
         } else if (BS == 2) {
-            const double det = D[0] * D[3] - D[1] * D[2];
-            Minv[n * 4 + 0] = D[3] / det; Minv[n * 4 + 1] = -D[1] / det;
-            Minv[n * 4 + 2] = -D[2] / det; Minv[n * 4 + 3] = D[0] / det;
+            // the diagonal block of K is symmetric up to rounding (it is summed from symmetric element blocks in a fixed order);
+            // the stored inverse is that of its symmetric part, so that M⁻¹ is exactly symmetric (PCG needs an SPD preconditioner)
+            const double o = 0.5 * (D[1] + D[2]);
+            const double det = D[0] * D[3] - o * o;
+            Minv[n * 3 + 0] = D[3] / det; Minv[n * 3 + 1] = -o / det; Minv[n * 3 + 2] = D[0] / det;
         } else {
-            const double c0 = D[4] * D[8] - D[5] * D[7], c1 = D[5] * D[6] - D[3] * D[8], c2 = D[3] * D[7] - D[4] * D[6];
-            const double det = D[0] * c0 + D[1] * c1 + D[2] * c2;
-            double *M = Minv + n * 9;
-            M[0] = c0 / det; M[1] = (D[2] * D[7] - D[1] * D[8]) / det; M[2] = (D[1] * D[5] - D[2] * D[4]) / det;
-            M[3] = c1 / det; M[4] = (D[0] * D[8] - D[2] * D[6]) / det; M[5] = (D[2] * D[3] - D[0] * D[5]) / det;
-            M[6] = c2 / det; M[7] = (D[1] * D[6] - D[0] * D[7]) / det; M[8] = (D[0] * D[4] - D[1] * D[3]) / det;
+            const double a01 = 0.5 * (D[1] + D[3]), a02 = 0.5 * (D[2] + D[6]), a12 = 0.5 * (D[5] + D[7]);
+            const double a00 = D[0], a11 = D[4], a22 = D[8];
+            const double c00 = a11 * a22 - a12 * a12, c01 = a02 * a12 - a01 * a22, c02 = a01 * a12 - a02 * a11;
+            const double det = a00 * c00 + a01 * c01 + a02 * c02;
+            double *M = Minv + n * 6;
+            M[0] = c00 / det; M[1] = c01 / det; M[2] = c02 / det;
+            M[3] = (a00 * a22 - a02 * a02) / det; M[4] = (a01 * a02 - a00 * a12) / det;
+            M[5] = (a00 * a11 - a01 * a01) / det;
         }
     }
 }

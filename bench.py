@@ -369,7 +369,9 @@ def main():
     # whole-iteration algorithmic bytes of this rank
     S = 14
     nip = nlocal_elems * model.nip
-    b_cg = spmv_bytes + nloc * (104 + 24)
+    # vector kernels per dof: update reads p,q,x,r (32) + M^-1 (16: symmetric 3x3 inverse per node; 8 Jacobi), writes x,r,z (24);
+    # p-update reads z,p and writes p (24)
+    b_cg = spmv_bytes + nloc * (56 + (16 if args.precond == 'block-jacobi' else 8) + 24)
     b_asm = nlocal_elems * 20 * 4 + 24 * nlocal_nodes + nip * 56 + nlocal_elems * 400 * 4 + 8 * nblk * nd * nd
     b_upd = nlocal_elems * 20 * 4 + 48 * nlocal_nodes + 2 * nip * 8 * S + 8 * nloc
     b_it = b_asm + b_upd + float(np.mean(cg_iters)) * b_cg + 2 * nip * 8 * S
