@@ -17,7 +17,7 @@ from oracle import oracle as O
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(autouse=True, params=["ebe-patch", "ebe-colour", "csr"])
+@pytest.fixture(autouse=True, params=["ebe-patch", "ebe-colour", "ebe-mixed", "csr"])
 def cg_operator(request, monkeypatch):
     """Multi-batch handles with every CG operator: the patch form of the matrix-free operator (forced on these small meshes),
     its colour-ordered form, and the block-CSR SpMV (what handles this small start with)."""
@@ -27,6 +27,9 @@ def cg_operator(request, monkeypatch):
         monkeypatch.setenv("AMARU_EBE_PATCH_MINPATCH", "0")
     elif request.param == "ebe-colour":
         monkeypatch.setenv("AMARU_EBE_PATCH", "0")
+    elif request.param == "ebe-mixed":               # batches with >= 2 patches take the patch form, the others the colour form
+        monkeypatch.setenv("AMARU_EBE_PATCH_MINFILL", "0")   # (HEX8 + TET10 model: one batch of each form in one handle)
+        monkeypatch.setenv("AMARU_EBE_PATCH_MINPATCH", "2")
     return request.param
 
 
