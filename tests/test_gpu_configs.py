@@ -191,3 +191,46 @@ def test_config5_hex8_2M_newmark_full_size():
     assert model.U[top, 2].mean() < 0 and model.V[top, 2].mean() < 0 and np.isfinite(model.A).all()
     # the load is carried by inertia at this time scale: sum(M*A) ~ applied resultant (damping and stiffness are small yet)
     assert all(s["cg_relres"] <= 1e-10 for s in ana.stats)
+
+
+def test_config3_footing_midsize_vs_oracle_pcg():
+    """config 3 at 32^3 HEX20 (32 768 elements, 418 k dofs — too large for the oracle's direct solve in test time): two chained
+    Newton iterations of the first increment against the oracle with its own Jacobi-PCG (orc_pcg_jacobi, OpenMP) standing in
+    for lu(K11): the second tangent is assembled on the plastic trial state the first one left.  u 1e-8, reactions / f_int /
+    stresses 1e-7, same plastic integration points; K spot-checked through products (1e-12)."""
+    from amaru_jl_b200 import lib as L
+    n = 32
+    mesh = Mesh(Block([[0, 0, 0], [1, 1, 1]], nx=n, ny=n, nz=n, cellshape="HEX20", tag="solids"))
+    model = FEModel(mesh, [("solids", MechSolid, VonMises, dict(E=210e6, nu=0.3, fy=240e3, H=0.0))], MechContext())
+    bcs = [("z==0", NodeBC(ux=0, uy=0, uz=0)), ("z==1 and x>=0.375 and x<=0.625 and y>=0.375 and y<=0.625", NodeBC(uz=-0.01))]
+    eqid, nu, setup = model.configure_dofs(bcs)
+    Uex, Fex = model.get_bc_vals(eqid, setup)
+    om = O.OracleModel(model.flatten(), eqid, eqid.size, nu)
+    dm = L.DeviceModel(model.flatten(), eqid, eqid.size, nu)
+    assert dm.spmv_kernel.startswith("k_ebe")                        # the default (matrix-free) operator at this size
+    rng = np.random.default_rng(2)
+    try:
+        for it in range(2):
+            dm.assemble_K()
+            st, K = om.mount_K()
+            assert st == 0
+            Kr = K.tocsr()
+            x = rng.uniform(-1, 1, eqid.size)
+            assert rel(dm.matvec(1.0, 0.0, x), Kr @ x) < 1e-12
+            dU, dF = 0.1 * Uex, 0.1 * Fex
+            U, F = dU.copy(), dF.copy()
+            iters, rr = dm.solve(U, F, cg_rtol=1e-12)
+            K11 = Kr[:nu, :nu]
+            xo, ito, rro = O.pcg_jacobi(K11, dF[:nu] - Kr[:nu, nu:] @ dU[nu:], rtol=1e-12)
+            Uo = dU.copy()
+            Uo[:nu] = xo
+            Fo = Kr[nu:, :] @ Uo
+            assert rro <= 2e-12 and rel(U, Uo) < 1e-8 and rel(F[nu:], Fo) < 1e-7
+            dFin = dm.update_state(Uo)                               # same input on both sides
+            dFo, st = om.update_state(Uo)
+            assert st == 0 and rel(dFin, dFo) < 1e-12
+            s = dm.get_state()
+            assert rel(s["sigma"], om.sig) < 1e-12 and np.array_equal(s["dlam"] > 0, om.dlam > 0)
+        assert (om.dlam > 0).sum() > 100
+    finally:
+        dm.close()
