@@ -715,7 +715,9 @@ int64_t amaru_ebe_bytes(const amaru_model *m) {
     for (size_t i = 0; i < m->batches.size(); i++) {
         const Batch &b = m->batches[i];
         bytes += (int64_t)8 * (b.nd * b.nd + 1) * b.nelem * b.nip;
-        if (E && E->b[i].patch) bytes += (int64_t)2 * b.nn * b.nelem + 4 * b.nelem;   // 16-bit patch-local node ids + element record
+        if (E && E->b[i].patch)   // stored format: lane-major packed 16-bit ids (one 64-bit word per lane, word and group), element
+            // records, node entries of the patches (4 B each)
+            bytes += (E->b[i].nslots / 8) * (int64_t)amaru_patch_id_words(b.nn) * 256 + 4 * E->b[i].nslots + 4 * E->b[i].pnode_total;
         else bytes += (int64_t)4 * b.nn * b.nelem + 5 * b.nelem;
     }
     bytes += 48 * (E ? E->nplastic_ip : 0);
