@@ -96,6 +96,21 @@ def test_elastic_quad4_planestress():
     assert np.abs(O.calcDe_planestress(E, nu)[2]).max() == 0.0
 
 
+# reference test/mech/elem/axisymmetric.jl:4-61 (the axisymmetric half; its 3D half needs `revolve`, outside the path):
+# solid cylinder r, y in [0, 1], E = 100, nu = 0.2, ty = -10 on top -> uniaxial state, (ux, uy)(1, 1) = (nu*10/E, -10/E)
+@pytest.mark.parametrize("shape", ["QUAD4", "QUAD8"])
+def test_axisymmetric_reference_case(shape):
+    mesh = Mesh(Block([[0, 0], [1, 1]], nx=4, ny=4, cellshape=shape, tag="solids"))
+    model = FEModel(mesh, [("solids", MechSolid, LinearElastic, dict(E=100.0, nu=0.2))], MechContext(stressmodel="axisymmetric"))
+    bcs = [("x==0", SurfaceBC(ux=0)), ("y==0", SurfaceBC(uy=0)), ("y==1", SurfaceBC(ty=-10))]
+    res, eqid, om = run(model, bcs, nincs=1)
+    assert res["success"]
+    U = res["U"][eqid]
+    node = model.select_nodes("x==1 && y==1")[0]
+    assert np.abs(U[node] - np.array([0.02, -0.1])).max() < 1e-10      # the reference holds its 3D twin to 1e-3
+    assert np.abs(om.sig - np.array([0, -10.0, 0, 0, 0, 0])).max() < 1e-9
+
+
 def test_axisymmetric_lame_cylinder():
     """stressmodel = :axisymmetric (hoop row of B, th = 2*pi*r: mech-solid.jl:94-108,143; distributed.jl:121) against the Lamé
     solution of a thick-walled cylinder (a = 1, b = 2) under internal pressure with plane-strain ends:
