@@ -37,6 +37,7 @@ def make(shape, n=3, jitter=0.0, thickness=1.0):
 def oracle_F(model, eqid, setup, t=0.0):
     """get_bc_vals restricted to the distributed loads, one entity at a time through the oracle."""
     nd = model.ndim
+    axi = model.ctx.stressmodel == "axisymmetric"
     F = np.zeros(eqid.size)
     for bc, target in setup:
         for key, val in bc.conds.items():
@@ -45,12 +46,12 @@ def oracle_F(model, eqid, setup, t=0.0):
                 sid = model.shape.facet_shape.id
                 X = OL.ip_coords(sid, model.coords, fn, nd)
                 vals = np.broadcast_to(evaluate(val, x=X[:, 0], y=X[:, 1], z=X[:, 2], t=t), (X.shape[0],))
-                OL.apply(sid, model.coords, fn, eqid, nd, model.thickness, ("tx", "ty", "tz", "tn").index(key), vals, F)
+                OL.apply(sid, model.coords, fn, eqid, nd, model.thickness, ("tx", "ty", "tz", "tn").index(key), vals, F, axi=axi)
             elif isinstance(bc, BodyC) and key in ("wx", "wy", "wz"):
                 nodes = model.conn[target]
                 X = OL.ip_coords(model.shape.id, model.coords, nodes, nd)
                 vals = np.broadcast_to(evaluate(val, x=X[:, 0], y=X[:, 1], z=X[:, 2]), (X.shape[0],))
-                OL.apply(model.shape.id, model.coords, nodes, eqid, nd, model.thickness, ("wx", "wy", "wz").index(key), vals, F)
+                OL.apply(model.shape.id, model.coords, nodes, eqid, nd, model.thickness, ("wx", "wy", "wz").index(key), vals, F, axi=axi)
     return F
 
 
@@ -104,6 +105,26 @@ def test_host_get_bc_vals_matches_oracle(shape, bcs):
     Fo = oracle_F(m, eqid, setup)
     assert np.abs(Fo).max() > 0
     assert np.abs(F - Fo).max() <= 1e-13 * np.abs(Fo).max()
+
+
+@pytest.mark.parametrize("shape", ["QUAD4", "QUAD8"])
+def test_axisymmetric_loads(shape):
+    """stressmodel = :axisymmetric: th = 2*pi*X[1] at every integration point of a facet / cell (distributed.jl:121,193).  The
+    host integration equals the oracle's, and the resultants are pressure x lateral area / weight of the revolved body."""
+    mesh = Mesh(Block([[1, 0], [3, 1]], nx=4, ny=3, cellshape=shape, tag="solids"))
+    m = FEModel(mesh, MATS, MechContext(stressmodel="axisymmetric"))
+    bcs = [("x==3", SurfaceBC(tx=-2.0)), ("y==1", SurfaceBC(ty="-0.5*x")), ("x>=0", BodyC(wy=-1.5))]
+    eqid, nu, setup = m.configure_dofs(bcs)
+    _, F = m.get_bc_vals(eqid, setup)
+    Fo = oracle_F(m, eqid, setup)
+    assert np.abs(F - Fo).max() <= 1e-13 * np.abs(Fo).max()
+    m1 = FEModel(mesh, MATS, MechContext(stressmodel="axisymmetric"))
+    eqid, nu, setup = m1.configure_dofs([("x==3", SurfaceBC(tx=-2.0))])
+    _, F1 = m1.get_bc_vals(eqid, setup)
+    assert abs(F1[eqid[:, 0]].sum() - (-2.0 * 2 * np.pi * 3 * 1)) < 1e-12        # pressure x (2 pi r h)
+    eqid, nu, setup = m1.configure_dofs([("x>=0", BodyC(wy=-1.5))])
+    _, F2 = m1.get_bc_vals(eqid, setup)
+    assert abs(F2[eqid[:, 1]].sum() - (-1.5 * np.pi * (9 - 1) * 1)) < 1e-11       # weight of the hollow cylinder
 
 
 def test_unsuitable_keys_are_refused():
